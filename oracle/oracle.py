@@ -1,0 +1,144 @@
+"""ctypes front-end of oracle/iso_oracle.c (TEST INFRASTRUCTURE ONLY, see that file's header).
+
+The functions mirror the reference's call surface on plain NumPy dictionaries ("state dicts" keyed by
+the reference's variable names, veros/variables.py) so parity tests read like the reference's:
+
+    oracle.isoneutral_diffusion_pre(st)          # veros/core/isoneutral/isoneutral.py:18
+    oracle.isoneutral_diffusion(st, "temp")      # veros/core/isoneutral/diffusion.py:286
+    oracle.isoneutral_skew_diffusion(st, "salt") # veros/core/isoneutral/diffusion.py:298
+    oracle.solve_implicit(a, b, c, d, water, edge, b_edge=None, d_edge=None)  # veros/core/utilities.py:51
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class OracleParams(ctypes.Structure):
+    _fields_ = [
+        ("N", ctypes.c_int32), ("M", ctypes.c_int32), ("nz", ctypes.c_int32),
+        ("eos_type", ctypes.c_int32), ("enable_conserve_energy", ctypes.c_int32),
+        ("tau", ctypes.c_int32), ("taup1", ctypes.c_int32), ("pad_", ctypes.c_int32),
+        ("K_iso_steep", ctypes.c_double), ("iso_slopec", ctypes.c_double), ("iso_dslope", ctypes.c_double),
+        ("dt_tracer", ctypes.c_double), ("grav", ctypes.c_double), ("rho_0", ctypes.c_double),
+    ]
+
+
+def build(force=False):
+    """Compile liboracle.so next to the source (gcc, a second or two)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "iso_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "liboracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+    return _LIB
+
+
+def _p(arr):
+    return None if arr is None else arr.ctypes.data_as(ctypes.c_void_p)
+
+
+def _f64(x):
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def _u8(x):
+    return np.ascontiguousarray(np.asarray(x).astype(np.uint8))
+
+
+def params_from_state(st):
+    N, M, nz = st["K_iso"].shape
+    return OracleParams(
+        N=N, M=M, nz=nz, eos_type=int(st["eq_of_state_type"]),
+        enable_conserve_energy=int(bool(st["enable_conserve_energy"])),
+        tau=int(st["tau"]), taup1=int(st["taup1"]), pad_=0,
+        K_iso_steep=float(st["K_iso_steep"]), iso_slopec=float(st["iso_slopec"]),
+        iso_dslope=float(st["iso_dslope"]), dt_tracer=float(st["dt_tracer"]),
+        grav=float(st["grav"]), rho_0=float(st["rho_0"]),
+    )
+
+
+_METRICS = ("dxt", "dxu", "dyt", "dyu", "cost", "cosu", "dzt", "dzw")
+
+
+def isoneutral_diffusion_pre(st):
+    """In place on st["Ai_*"], st["K_11|K_22|K_33"] (only the reference's write regions change)."""
+    P = params_from_state(st)
+    for k in ("Ai_ez", "Ai_nz", "Ai_bx", "Ai_by", "K_11", "K_22", "K_33"):
+        st[k] = _f64(st[k]).copy()
+    args = [_f64(st["temp"]), _f64(st["salt"]), _f64(st["K_iso"])]
+    args += [_u8(st[m]) for m in ("maskT", "maskU", "maskV", "maskW")]
+    args += [_f64(st[m]) for m in _METRICS] + [_f64(st["zt"])]
+    outs = [st[k] for k in ("Ai_ez", "Ai_nz", "Ai_bx", "Ai_by", "K_11", "K_22", "K_33")]
+    lib().oracle_iso_pre(ctypes.byref(P), *[_p(a) for a in args + outs])
+    return st
+
+
+def _diffusion(st, tracer, iso, tdma_mode=0):
+    P = params_from_state(st)
+    istemp = tracer == "temp"
+    dname = "dtemp_iso" if istemp else "dsalt_iso"
+    pname = "P_diss_iso" if iso else "P_diss_skew"
+    xname = "int_drhodT" if istemp else "int_drhodS"
+    st[tracer] = _f64(st[tracer]).copy()
+    st[dname] = _f64(st[dname]).copy()
+    energy = bool(st["enable_conserve_energy"])
+    if energy:
+        st[pname] = _f64(st[pname]).copy()
+    shape = st["K_iso"].shape
+    fe, fn, ft = (np.zeros(shape) for _ in range(3))
+    kfield = _f64(st["K_iso"] if iso else st["K_gm"])
+    args = [st[tracer], st[dname], kfield] + [_f64(st[k]) for k in ("Ai_ez", "Ai_nz", "Ai_bx", "Ai_by", "K_11", "K_22", "K_33")]
+    args += [_u8(st["maskT"]), _u8(st["maskW"]), np.ascontiguousarray(st["kbot"], dtype=np.int32)]
+    args += [_f64(st[m]) for m in _METRICS]
+    args += [_f64(st[xname]) if energy else None, st[pname] if energy else None, fe, fn, ft]
+    lib().oracle_iso_diffusion(ctypes.byref(P), ctypes.c_int32(int(iso)), *[_p(a) for a in args],
+                               ctypes.c_int32(tdma_mode))
+    st["flux_east"], st["flux_north"], st["flux_top"] = fe, fn, ft
+    return st
+
+
+def isoneutral_diffusion(st, tracer, tdma_mode=0):
+    return _diffusion(st, tracer, True, tdma_mode)
+
+
+def isoneutral_skew_diffusion(st, tracer):
+    return _diffusion(st, tracer, False)
+
+
+def isoneutral_step(st, tdma_mode=0):
+    """thermodynamics.py:430-432: pre, then T, then S."""
+    isoneutral_diffusion_pre(st)
+    isoneutral_diffusion(st, "temp", tdma_mode)
+    isoneutral_diffusion(st, "salt", tdma_mode)
+    return st
+
+
+def solve_implicit(a, b, c, d, water_mask, edge_mask, b_edge=None, d_edge=None, mode=0):
+    """mode 0: dgtsv (no-pivot) operation order; mode 1: Thomas cp/dp recurrence."""
+    a, b, c, d = map(_f64, (a, b, c, d))
+    nz = a.shape[-1]
+    ncol = a.size // nz if nz else 0
+    out = np.zeros(a.shape)
+    if a.size == 0:
+        return out
+    be = None if b_edge is None else _f64(b_edge)
+    de = None if d_edge is None else _f64(d_edge)
+    lib().oracle_solve_implicit(ctypes.c_int64(ncol), ctypes.c_int32(nz), _p(a), _p(b), _p(c), _p(d),
+                                _p(_u8(water_mask)), _p(_u8(edge_mask)), _p(be), _p(de), _p(out),
+                                ctypes.c_int32(mode))
+    return out
+
+
+def solve_tridiagonal(a, b, c, d, water_mask, edge_mask, mode=0):
+    return solve_implicit(a, b, c, d, water_mask, edge_mask, mode=mode)
