@@ -1,0 +1,159 @@
+/*
+ * veros_b200.h -- C ABI of libveros_b200.so: sm_100a CUDA implementation of Veros's isoneutral
+ * mixing step and column (tridiagonal) solve.
+ *
+ * Every compute entry point has the signature of a *legacy XLA GPU custom call* (api_version 0),
+ * the mechanism the reference uses for its one native op:
+ *
+ *     void f(cudaStream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+ *
+ *   reference declaration   veros/core/special/cuda_tdma_kernels.h:10-11
+ *   reference registration  veros/core/special/tdma_.py:34-37
+ *                           jax.ffi.register_ffi_target(name, PyCapsule("xla._CUSTOM_CALL_TARGET"),
+ *                                                       platform="CUDA", api_version=0)
+ *   reference capsule       veros/core/special/tdma_cuda_.pyx:23-30
+ *
+ * `buffers` holds device pointers: all operands in order, then all results in order.  In/out state
+ * (Ai_*, K_*, tracers, tendencies, P_diss) appears once as an operand and once as a result; the
+ * intended use is operand_output_aliases (same pointer twice).  If the two pointers differ the op
+ * first copies operand -> result on `stream`, so it is also correct without aliasing.
+ * `opaque` is the raw bytes of one of the POD descriptors below (length-checked).
+ * A trailing 5th argument (XlaCustomCallStatus*) passed by newer XLA versions is ignored.
+ *
+ * The ops only ENQUEUE work on `stream`: no allocation, no synchronisation, no retained state.
+ * Errors (bad descriptor, failed launch) never throw or exit: they are printed to stderr and
+ * latched; read them with veros_b200_last_error().  (The reference exits the process instead,
+ * cuda_tdma_kernels.cu:9-17,72-79.)
+ *
+ * Array conventions (veros/variables.py:75-162): C order, z fastest; N = nx+4, M = ny+4 include the
+ * two ghost cells per side; float64; masks are 1-byte bool; kbot/tau/taup1 are int32.
+ * Tracers are (N,M,nz,3) with the time level last; Ai_* are (N,M,nz,2,2).
+ */
+#ifndef VEROS_B200_H
+#define VEROS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VEROS_B200_ABI_VERSION 1
+
+/* ---------------------------------------------------------------- descriptors (opaque payloads) */
+
+/* Same layout as the reference's TridiagDescriptor (cuda_tdma_kernels.h:5-8,
+ * tdma_cuda_.pyx:18-20 build_tridiag_descriptor). */
+typedef struct VerosB200TridiagDescriptor {
+    int32_t num_systems;  /* number of columns = prod(shape[:-1]) */
+    int32_t system_depth; /* nz */
+} VerosB200TridiagDescriptor;
+
+#define VEROS_B200_HAS_B_EDGE 1
+#define VEROS_B200_HAS_D_EDGE 2
+
+typedef struct VerosB200SolveDescriptor {
+    int32_t num_systems;
+    int32_t system_depth;
+    int32_t flags; /* VEROS_B200_HAS_B_EDGE | VEROS_B200_HAS_D_EDGE */
+    int32_t reserved;
+} VerosB200SolveDescriptor;
+
+#define VEROS_B200_FLAG_SKEW 1 /* iso_diffusion: isoneutral_skew_diffusion (K1=-K_gm, K2=K_gm) */
+
+/* Static (jit-constant) facts of the isoneutral ops: shapes and the settings of
+ * veros/settings.py:24-91 that the path reads. */
+typedef struct VerosB200IsoDescriptor {
+    int32_t nx_tot; /* N = nx + 4 (local slab, ghosts included) */
+    int32_t ny_tot; /* M = ny + 4 */
+    int32_t nz;
+    int32_t eq_of_state_type;       /* 1..5, veros/core/density/get_rho.py:93-131 */
+    int32_t enable_conserve_energy; /* settings.enable_conserve_energy */
+    int32_t flags;                  /* VEROS_B200_FLAG_* */
+    double K_iso_steep;
+    double iso_slopec;
+    double iso_dslope;
+    double dt_tracer;
+    double grav;
+    double rho_0;
+} VerosB200IsoDescriptor;
+
+/* ------------------------------------------------------------------------------ compute ops */
+
+/* Column solve on the model's native (X,Y,nz) z-contiguous layout, replacing
+ * veros.core.utilities.solve_implicit (utilities.py:51-59) + operators.solve_tridiagonal
+ * (operators.py:60-77 NumPy/dgtsv, :103-156 JAX) + special.tdma_ (tdma_.py:49-68).
+ * Per column it executes LAPACK dgtsv's operation sequence (partial pivoting included), i.e. it is
+ * bit-identical to the reference's NumPy backend; rows outside water_mask give 0.
+ * opaque: VerosB200SolveDescriptor.
+ * buffers: 0 a, 1 b, 2 c, 3 d (f64 [ncol][nz]), 4 water_mask, 5 edge_mask (u8 [ncol][nz]),
+ *          6 b_edge, 7 d_edge (f64; ignored unless flagged, pass any valid pointer) | 8 out (f64). */
+void veros_b200_solve_implicit_f64(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
+/* Drop-in for the reference's own CUDA targets "tdma_cuda_double" / "tdma_cuda_float"
+ * (cuda_tdma_kernels.cu:81-111): pre-masked diagonals in the z-major layout requested by
+ * tdma_.py:167-180, Thomas recurrence without pivoting.
+ * opaque: VerosB200TridiagDescriptor.  buffers: 0 a, 1 b, 2 c, 3 d | 4 out, 5 workspace. */
+void veros_b200_tdma_zmajor_f64(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+void veros_b200_tdma_zmajor_f32(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
+/* veros.core.isoneutral.isoneutral_diffusion_pre (isoneutral/isoneutral.py:18-229).
+ * opaque: VerosB200IsoDescriptor.
+ * buffers (operands): 0 temp, 1 salt (N,M,nz,3), 2 tau (int32[1]), 3 K_iso,
+ *          4 maskT, 5 maskU, 6 maskV, 7 maskW (u8), 8 dxt, 9 dxu (N), 10 dyt, 11 dyu, 12 cost,
+ *          13 cosu (M), 14 dzt, 15 dzw, 16 zt (nz),
+ *          17 Ai_ez, 18 Ai_nz, 19 Ai_bx, 20 Ai_by, 21 K_11, 22 K_22, 23 K_33   (previous values)
+ * (results): 24 Ai_ez, 25 Ai_nz, 26 Ai_bx, 27 Ai_by, 28 K_11, 29 K_22, 30 K_33,
+ *          31 workspace (veros_b200_iso_pre_workspace_bytes) */
+void veros_b200_iso_pre_f64(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
+/* veros.core.isoneutral.isoneutral_diffusion / isoneutral_skew_diffusion for ONE tracer
+ * (isoneutral/diffusion.py:9-307; veros/core/diffusion.py:9-62 for the dissipation).
+ * opaque: VerosB200IsoDescriptor (flags: VEROS_B200_FLAG_SKEW selects the skew variant).
+ * buffers (operands): 0 tr (N,M,nz,3), 1 dtracer_iso, 2 P_diss (iso: P_diss_iso, skew: P_diss_skew),
+ *          3 tau, 4 taup1 (int32[1]), 5 K (iso: K_iso, skew: K_gm),
+ *          6 Ai_ez, 7 Ai_nz, 8 Ai_bx, 9 Ai_by, 10 K_11, 11 K_22, 12 K_33, 13 maskT, 14 maskW (u8),
+ *          15 kbot (int32 N,M), 16 dxt, 17 dxu, 18 dyt, 19 dyu, 20 cost, 21 cosu, 22 dzt, 23 dzw,
+ *          24 int_drhodX (N,M,nz,3; int_drhodT for temp, int_drhodS for salt)
+ * (results): 25 tr, 26 dtracer_iso, 27 P_diss, 28 workspace (veros_b200_iso_diffusion_workspace_bytes)
+ * With enable_conserve_energy == 0 buffers 2, 24, 27 are not touched (pass any valid pointer).
+ * Bit-identical to the reference's NumPy backend on identical inputs. */
+void veros_b200_iso_diffusion_f64(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
+/* One complete neutral-diffusion step, veros/core/thermodynamics.py:430-432:
+ *   isoneutral_diffusion_pre; isoneutral_diffusion(temp); isoneutral_diffusion(salt)
+ * with the two tracer updates sharing one factorisation of the K_33 column matrix.
+ * opaque: VerosB200IsoDescriptor.
+ * buffers (operands): 0 temp, 1 salt, 2 dtemp_iso, 3 dsalt_iso, 4 P_diss_iso,
+ *          5 Ai_ez, 6 Ai_nz, 7 Ai_bx, 8 Ai_by, 9 K_11, 10 K_22, 11 K_33,
+ *          12 tau, 13 taup1, 14 K_iso, 15 maskT, 16 maskU, 17 maskV, 18 maskW, 19 kbot,
+ *          20 dxt, 21 dxu, 22 dyt, 23 dyu, 24 cost, 25 cosu, 26 dzt, 27 dzw, 28 zt,
+ *          29 int_drhodT, 30 int_drhodS
+ * (results): 31..42 = operands 0..11, 43 workspace (veros_b200_iso_step_workspace_bytes) */
+void veros_b200_iso_step_f64(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
+/* ------------------------------------------------------------------------ host-side helpers */
+
+/* Scratch the caller must provide as the last result (0 is possible; then pass any valid pointer). */
+size_t veros_b200_iso_pre_workspace_bytes(const char* opaque, size_t opaque_len);
+size_t veros_b200_iso_diffusion_workspace_bytes(const char* opaque, size_t opaque_len);
+size_t veros_b200_iso_step_workspace_bytes(const char* opaque, size_t opaque_len);
+
+/* Sticky error state: 0 = ok; otherwise a cudaError_t value or VEROS_B200_ERR_*. */
+#define VEROS_B200_ERR_BAD_DESCRIPTOR 100001
+#define VEROS_B200_ERR_BAD_ARGUMENT 100002
+int veros_b200_last_error(void);
+const char* veros_b200_last_error_string(void);
+void veros_b200_clear_error(void);
+
+int veros_b200_abi_version(void);
+/* sizeof() of descriptor 0 = Tridiag, 1 = Solve, 2 = Iso as compiled into the library. */
+size_t veros_b200_descriptor_size(int which);
+/* Number of kernel launches enqueued by this library since load (bench.py's gpu_launches). */
+unsigned long long veros_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VEROS_B200_H */

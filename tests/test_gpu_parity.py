@@ -1,0 +1,376 @@
+"""Parity of the CUDA path (through the C ABI of libveros_b200.so) with
+  (a) golden vectors produced by the reference's NumPy implementation (tests/golden/*.npz), and
+  (b) the CPU oracle (oracle/iso_oracle.c, itself pinned to (a)) on seeded synthetic states.
+
+Tolerances (BASELINE.json north_star: 1e-12 relative on diffusivities and tracer tendencies):
+  * isoneutral_diffusion / skew / solve_tridiagonal on identical inputs: BIT-EXACT.
+  * isoneutral_diffusion_pre: max|x-ref|/max|ref| <= 1e-12 per field (measured ~1e-15; exactness is
+    impossible: NumPy's SIMD tanh and any other tanh differ in the last bit).
+  * chained step (pre -> T -> S): tracers <= 1e-12 normalised; tendencies <= 1e-12 in the form
+    dt*max|d(dtracer)|/max|tracer| ((new-old)/dt cancels ~10 digits, so ulp-level
+    differences of K_33 from tanh show up at 1e-11 of max|dtracer| in any implementation).
+"""
+import numpy as np
+import pytest
+
+from helpers import AI, KS, copy_state, golden_names, load_golden, norm_err, tendency_err
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+NAMES = golden_names()
+PRE_TOL = 1e-12
+STEP_TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def gpu_state(st, dev):
+    from veros_b200.state import IsoState
+
+    return IsoState.from_numpy(st, dev)
+
+
+def run_pre(st, dev):
+    from veros_b200 import isoneutral
+
+    gs = gpu_state(st, dev)
+    out = isoneutral.isoneutral_diffusion_pre(gs)
+    gs.variables.update(out)
+    torch.cuda.synchronize()
+    return gs
+
+
+# ------------------------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("name", NAMES)
+def test_pre_vs_reference_golden(name, dev):
+    st, stages = load_golden(name)
+    gs = run_pre(st, dev)
+    got = gs.to_numpy(AI + KS)
+    for k in AI + KS:
+        err = norm_err(got[k], stages["pre"][k])
+        assert err <= PRE_TOL, (k, err)
+    # write-region fidelity: untouched elements keep their previous values exactly
+    for k in AI:
+        prev, ref = st[k], stages["pre"][k]
+        untouched = ref == prev
+        assert np.array_equal(got[k][untouched], prev[untouched]), k
+    assert np.all(got["K_33"][:, :, -1] == 0.0)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_diffusion_bitexact_vs_reference_golden(name, dev):
+    from veros_b200 import isoneutral
+
+    st, stages = load_golden(name)
+    for k in AI + KS:  # identical inputs: the reference's own pre outputs
+        st[k] = stages["pre"][k].copy()
+    energy = bool(st["enable_conserve_energy"])
+    gs = gpu_state(st, dev)
+    vs = gs.variables
+    isoneutral.isoneutral_diffusion(gs, vs.temp, True)
+    got = gs.to_numpy(["temp", "dtemp_iso"] + (["P_diss_iso"] if energy else []))
+    assert np.array_equal(got["temp"], stages["dT"]["temp"])
+    assert np.array_equal(got["dtemp_iso"], stages["dT"]["dtemp_iso"])
+    if energy:
+        assert np.array_equal(got["P_diss_iso"], stages["dT"]["P_diss_iso"])
+    isoneutral.isoneutral_diffusion(gs, vs.salt, False)
+    got = gs.to_numpy(["salt", "dsalt_iso"] + (["P_diss_iso"] if energy else []))
+    assert np.array_equal(got["salt"], stages["dS"]["salt"])
+    assert np.array_equal(got["dsalt_iso"], stages["dS"]["dsalt_iso"])
+    if energy:
+        assert np.array_equal(got["P_diss_iso"], stages["dS"]["P_diss_iso"])
+    isoneutral.isoneutral_skew_diffusion(gs, vs.temp, True)
+    isoneutral.isoneutral_skew_diffusion(gs, vs.salt, False)
+    got = gs.to_numpy(["temp", "salt", "dtemp_iso", "dsalt_iso"] + (["P_diss_skew"] if energy else []))
+    assert np.array_equal(got["temp"], stages["kS"]["temp"] if "temp" in stages["kS"] else stages["kT"]["temp"])
+    assert np.array_equal(got["salt"], stages["kS"]["salt"])
+    assert np.array_equal(got["dtemp_iso"], stages["kT"]["dtemp_iso"])
+    assert np.array_equal(got["dsalt_iso"], stages["kS"]["dsalt_iso"])
+    if energy:
+        assert np.array_equal(got["P_diss_skew"], stages["kS"]["P_diss_skew"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_solve_tridiagonal_bitexact_vs_reference_golden(name, dev):
+    from veros_b200 import utilities
+
+    _, stages = load_golden(name)
+    t = stages["tdma"]
+    args = [torch.from_numpy(np.ascontiguousarray(t[k])).to(dev) for k in ("a", "b", "c", "d", "water_mask", "edge_mask")]
+    out = utilities.solve_tridiagonal(*args).cpu().numpy()
+    assert np.array_equal(out, t["out"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_fused_step_vs_reference_golden(name, dev):
+    from veros_b200 import isoneutral
+
+    st, stages = load_golden(name)
+    energy = bool(st["enable_conserve_energy"])
+    gs = gpu_state(st, dev)
+    isoneutral.isoneutral_step(gs)
+    got = gs.to_numpy()
+    dt = float(st["dt_tracer"])
+    for k in AI + KS:
+        assert norm_err(got[k], stages["pre"][k]) <= PRE_TOL, k
+    assert norm_err(got["temp"], stages["dT"]["temp"]) <= STEP_TOL
+    assert norm_err(got["salt"], stages["dS"]["salt"]) <= STEP_TOL
+    assert tendency_err(got["dtemp_iso"], stages["dT"]["dtemp_iso"], dt, st["temp"]) <= STEP_TOL
+    assert tendency_err(got["dsalt_iso"], stages["dS"]["dsalt_iso"], dt, st["salt"]) <= STEP_TOL
+    if energy:
+        # P_diss_iso contains K_33 * d(tr_new)/dz: differences of O(1) tracers over one level
+        assert norm_err(got["P_diss_iso"], stages["dS"]["P_diss_iso"]) <= 1e-10
+
+
+# ------------------------------------------------------------------------------------ versus the oracle
+CASES = [
+    ("bench_1M", dict(nx=48, ny=40, nz=50)),
+    ("bench_1M", dict(nx=33, ny=21, nz=17, eq_of_state_type=3, enable_cyclic_x=True)),
+    ("bench_1M", dict(nx=20, ny=24, nz=33, eq_of_state_type=5)),
+    ("bench_1M", dict(nx=16, ny=16, nz=4, eq_of_state_type=2, enable_conserve_energy=False)),
+    ("global_4deg", {}),
+    ("acc", {}),
+    ("global_1deg", dict(nx=24, ny=40)),  # 1 degree column depth (nz = 115), reduced horizontally
+    ("global_025deg", dict(nx=16, ny=24)),  # nz = 80
+]
+
+
+@pytest.mark.parametrize("workload,kw", CASES)
+def test_ops_vs_oracle(workload, kw, dev):
+    from oracle import oracle
+    from veros_b200 import isoneutral, synthetic
+
+    st = synthetic.make_workload(workload, **kw)
+    ref = copy_state(st)
+    energy = bool(st["enable_conserve_energy"])
+    dt = float(st["dt_tracer"])
+
+    # pre
+    oracle.isoneutral_diffusion_pre(ref)
+    gs = run_pre(st, dev)
+    got = gs.to_numpy(AI + KS)
+    for k in AI + KS:
+        assert norm_err(got[k], ref[k]) <= PRE_TOL, k
+
+    # diffusion T, S and skew on identical inputs (the oracle's pre outputs): bit-exact
+    st2 = copy_state(ref)
+    gs = gpu_state(st2, dev)
+    vs = gs.variables
+    for tracer, istemp in (("temp", True), ("salt", False)):
+        oracle.isoneutral_diffusion(ref, tracer)
+        isoneutral.isoneutral_diffusion(gs, getattr(vs, tracer), istemp)
+    names = ["temp", "salt", "dtemp_iso", "dsalt_iso"] + (["P_diss_iso"] if energy else [])
+    got = gs.to_numpy(names)
+    for k in names:
+        assert np.array_equal(got[k], ref[k]), k
+    for tracer, istemp in (("temp", True), ("salt", False)):
+        oracle.isoneutral_skew_diffusion(ref, tracer)
+        isoneutral.isoneutral_skew_diffusion(gs, getattr(vs, tracer), istemp)
+    names = ["temp", "salt", "dtemp_iso", "dsalt_iso"] + (["P_diss_skew"] if energy else [])
+    got = gs.to_numpy(names)
+    for k in names:
+        assert np.array_equal(got[k], ref[k]), k
+
+    # fused step from the original state
+    ref2 = copy_state(st)
+    oracle.isoneutral_step(ref2)
+    gs = gpu_state(st, dev)
+    isoneutral.isoneutral_step(gs)
+    got = gs.to_numpy()
+    assert norm_err(got["temp"], ref2["temp"]) <= STEP_TOL
+    assert norm_err(got["salt"], ref2["salt"]) <= STEP_TOL
+    assert tendency_err(got["dtemp_iso"], ref2["dtemp_iso"], dt, st["temp"]) <= STEP_TOL
+    assert tendency_err(got["dsalt_iso"], ref2["dsalt_iso"], dt, st["salt"]) <= STEP_TOL
+
+
+def test_fused_step_equals_separate_ops(dev):
+    """The one-op step must be bit-identical to pre; diffusion(temp); diffusion(salt)."""
+    from veros_b200 import isoneutral, synthetic
+
+    st = synthetic.make_workload("global_1deg", nx=20, ny=16)
+    a, b = gpu_state(st, dev), gpu_state(st, dev)
+    isoneutral.isoneutral_step(a)
+    b.variables.update(isoneutral.isoneutral_diffusion_pre(b))
+    isoneutral.isoneutral_diffusion(b, b.variables.temp, True)
+    isoneutral.isoneutral_diffusion(b, b.variables.salt, False)
+    ga, gb = a.to_numpy(), b.to_numpy()
+    for k in AI + KS + ("temp", "salt", "dtemp_iso", "dsalt_iso", "P_diss_iso"):
+        assert np.array_equal(ga[k], gb[k]), k
+
+
+# ------------------------------------------------------------------------------------ column solve
+def _random_systems(nx, ny, nz, rng):
+    a, b, c, d = rng.standard_normal((4, nx, ny, nz))
+    kbot = rng.integers(0, nz, size=(nx, ny))
+    ks = kbot - 1
+    kk = np.arange(nz)[None, None, :]
+    land = (ks >= 0)[..., None]
+    return a, b, c, d, land & (kk >= ks[..., None]), land & (kk == ks[..., None])
+
+
+def test_random_systems_bitexact_vs_scipy_dgtsv(dev):
+    """Inputs of test/pyom_consistency/tridiag_test.py:8-37; compared with SciPy's LAPACK dgtsv called
+    exactly as veros/core/operators.py:60-77 calls it (pivoting happens on these systems)."""
+    from scipy.linalg import lapack
+    from veros_b200 import utilities
+
+    rng = np.random.default_rng(17)
+    a, b, c, d, water, edge = _random_systems(70, 60, 50, rng)
+    aa, cc = a.copy(), c.copy()
+    aa[edge] = 0
+    cc[..., -1] = 0
+    ref = np.zeros_like(a)
+    ref[water] = lapack.dgtsv(aa[water][1:], b[water], cc[water][:-1], d[water])[3]
+    args = [torch.from_numpy(x).to(dev) for x in (a, b, c, d, water, edge)]
+    out = utilities.solve_tridiagonal(*args).cpu().numpy()
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 2), (3, 5, 15), (7, 4, 115), (64, 64, 80), (5, 3, 1)])
+def test_solve_implicit_vs_oracle(shape, dev):
+    from oracle import oracle
+    from veros_b200 import utilities
+
+    rng = np.random.default_rng(5)
+    nx, ny, nz = shape
+    a, b, c, d, water, edge = _random_systems(nx, ny, nz, rng)
+    b = 3.0 + np.abs(b)  # model-like, diagonally dominant
+    b_edge, d_edge = 2.0 + np.abs(rng.standard_normal((nx, ny, nz))), rng.standard_normal((nx, ny, nz))
+    targs = [torch.from_numpy(x).to(dev) for x in (a, b, c, d, water, edge, b_edge, d_edge)]
+    for use_b, use_d in ((True, True), (True, False), (False, False)):
+        ref = oracle.solve_implicit(a, b, c, d, water, edge, b_edge if use_b else None, d_edge if use_d else None)
+        out = utilities.solve_implicit(*targs[:6], b_edge=targs[6] if use_b else None,
+                                       d_edge=targs[7] if use_d else None).cpu().numpy()
+        assert np.array_equal(out, ref)
+
+
+def test_solve_implicit_empty_and_errors(dev):
+    from veros_b200 import utilities
+
+    z = torch.zeros((0, 3, 5), dtype=torch.float64, device=dev)
+    m = torch.zeros((0, 3, 5), dtype=torch.bool, device=dev)
+    assert utilities.solve_implicit(z, z, z, z, m, m).shape == (0, 3, 5)
+    x = torch.zeros((2, 3, 5), dtype=torch.float64, device=dev)
+    mm = torch.zeros((2, 3, 5), dtype=torch.bool, device=dev)
+    with pytest.raises(ValueError):
+        utilities.solve_implicit(x, x[:1], x, x, mm, mm)
+    with pytest.raises(TypeError):
+        utilities.solve_implicit(*(x.float(),) * 4, mm, mm)
+    with pytest.raises(RuntimeError):
+        utilities.solve_implicit(*(x.cpu(),) * 4, mm.cpu(), mm.cpu())
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_tdma_zmajor_matches_thomas(dtype, dev):
+    """The reference-compatible z-major target (cuda_tdma_kernels.cu:19-70 contract) against the Thomas
+    recurrence of tdma_cython_.pyx:8-25 (oracle mode 1), masks pre-applied as tdma_.py:63-66 does."""
+    from oracle import oracle
+    from veros_b200 import utilities
+
+    rng = np.random.default_rng(11)
+    nx, ny, nz = 31, 17, 50
+    a, b, c, d, water, edge = _random_systems(nx, ny, nz, rng)
+    b = 3.0 + np.abs(b)
+    am = water * a * ~edge
+    bm = np.where(water, b, 1.0)
+    cm = water * c
+    dm = water * d
+    ref = oracle.solve_tridiagonal(a, b, c, d, water, edge, mode=1)
+    tdt = getattr(torch, dtype)
+    ops = [torch.from_numpy(x).to(dev).to(tdt).permute(2, 0, 1).contiguous().permute(1, 2, 0) for x in (am, bm, cm, dm)]
+    out = utilities.tdma_zmajor(*ops).cpu().numpy()
+    if dtype == "float64":
+        assert np.array_equal(out, ref)
+    else:
+        np.testing.assert_allclose(out, ref, rtol=2e-5, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------ ABI behaviour
+def test_non_aliased_buffers_give_same_result(dev):
+    """operand != result pointers (no operand_output_aliases): the op copies operand -> result first."""
+    from veros_b200 import _lib, isoneutral, synthetic
+
+    st = synthetic.make_workload("bench_1M", nx=12, ny=10, nz=9)
+    a = gpu_state(st, dev)
+    isoneutral.isoneutral_diffusion_pre(a)
+    ref = a.to_numpy(AI + KS)
+
+    b = gpu_state(st, dev)
+    vs = b.variables
+    names = ("Ai_ez", "Ai_nz", "Ai_bx", "Ai_by", "K_11", "K_22", "K_33")
+    results = [torch.full_like(getattr(vs, n), float("nan")) for n in names]
+    desc = isoneutral._descriptor(b)
+    ws = b.workspace(8)
+    operands = [vs.temp, vs.salt, vs.tau, vs.K_iso, vs.maskT, vs.maskU, vs.maskV, vs.maskW]
+    operands += [getattr(vs, n) for n in isoneutral._METRICS] + [vs.zt] + [getattr(vs, n) for n in names]
+    _lib.call("veros_b200_iso_pre_f64", [int(t.data_ptr()) for t in operands + results + [ws]], desc,
+              torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize()
+    for n, r in zip(names, results):
+        assert np.array_equal(r.cpu().numpy(), ref[n]), n
+        assert np.array_equal(getattr(vs, n).cpu().numpy(), st[n]), n  # operands untouched
+
+
+def test_bad_descriptor_raises(dev):
+    from veros_b200 import _lib
+
+    with pytest.raises(RuntimeError, match="bad descriptor"):
+        _lib.call("veros_b200_iso_step_f64", [0] * 44, b"\x00" * 7, 0)
+    bad = _lib.IsoDescriptor(nx_tot=3, ny_tot=9, nz=5, eq_of_state_type=1, iso_dslope=1.0, dt_tracer=1.0)
+    with pytest.raises(RuntimeError, match="bad argument"):
+        _lib.call("veros_b200_iso_pre_f64", [0] * 32, bad, 0)
+
+
+def test_runs_on_side_stream(dev):
+    from veros_b200 import isoneutral, synthetic
+
+    st = synthetic.make_workload("global_4deg")
+    a, b = gpu_state(st, dev), gpu_state(st, dev)
+    isoneutral.isoneutral_step(a)
+    s = torch.cuda.Stream(dev)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        isoneutral.isoneutral_step(b)
+    s.synchronize()
+    torch.cuda.synchronize()
+    ga, gb = a.to_numpy(), b.to_numpy()
+    for k in ("temp", "salt", "K_33", "Ai_by", "P_diss_iso"):
+        assert np.array_equal(ga[k], gb[k]), k
+
+
+# ------------------------------------------------------------------------------------ full-size properties
+def test_full_size_slab_invariance_and_invariants(dev):
+    """BASELINE full size (global_1deg 360x160x115): the interior of an x-slab computed with its
+    2-cell halos is bit-identical to the same cells of the global run (no hidden coupling), land
+    columns are untouched, K_33's top level is zero, ghost cells keep their values."""
+    from veros_b200 import isoneutral, synthetic
+
+    nxg = 360
+    st = synthetic.make_workload("global_1deg")
+    g = gpu_state(st, dev)
+    isoneutral.isoneutral_step(g)
+    full = g.to_numpy(["temp", "salt", "dtemp_iso", "K_33", "K_11", "Ai_bx"])
+    del g
+    torch.cuda.empty_cache()
+    assert np.all(np.isfinite(full["temp"]))
+    assert np.all(full["K_33"][:, :, -1] == 0.0)
+    land = st["kbot"] == 0
+    assert np.array_equal(full["temp"][land], st["temp"][land])
+    for arr in ("temp", "salt"):
+        assert np.array_equal(full[arr][:2], st[arr][:2]) and np.array_equal(full[arr][:, :2], st[arr][:, :2])
+    # slab [90, 180): local arrays = global[90 : 180 + 4]
+    x0, nxl = 90, 90
+    sl = synthetic.make_workload("global_1deg", nx=nxl, x_offset=x0, nx_global=nxg)
+    for k in ("temp", "kbot", "K_iso"):
+        assert np.array_equal(sl[k], st[k][x0:x0 + nxl + 4]), k
+    s = gpu_state(sl, dev)
+    isoneutral.isoneutral_step(s)
+    part = s.to_numpy(["temp", "salt", "dtemp_iso", "K_33", "K_11", "Ai_bx"])
+    for k, v in part.items():
+        assert np.array_equal(v[2:-2], full[k][x0 + 2:x0 + nxl + 2]), k

@@ -1,0 +1,68 @@
+// Shared declarations of libveros_b200: kernel launch wrappers, error latch, index helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/veros_b200.h"
+
+namespace vb {
+
+// ---- error latch (api.cu) -------------------------------------------------------------------
+void set_error(int code, const char* what);
+void count_launch(int n = 1);
+bool check_launch(const char* what);  // cudaPeekAtLastError -> latch; true if ok
+
+// ---- pointers of one isoneutral problem (all device memory) -------------------------------------
+struct Grid {
+    int N, M, nz;
+    const double *dxt, *dxu;          // (N)
+    const double *dyt, *dyu, *cost, *cosu;  // (M)
+    const double *dzt, *dzw, *zt;     // (nz)
+};
+
+struct PreArgs {
+    Grid g;
+    const double *temp, *salt;  // (N,M,nz,3)
+    const int32_t* tau;
+    const double* K_iso;
+    const uint8_t *maskT, *maskU, *maskV, *maskW;
+    double *Ai_ez, *Ai_nz, *Ai_bx, *Ai_by, *K_11, *K_22, *K_33;
+    double *drdT, *drdS;  // workspace, EOS 5 only
+    int eos;
+    double K_iso_steep, iso_slopec, iso_dslope;
+};
+
+struct DiffTracer {
+    double* tr;              // (N,M,nz,3) in/out (taup1 level written)
+    double* dtracer;         // (N,M,nz) in/out
+    const double* int_drhodX;  // (N,M,nz,3)
+};
+
+struct DiffArgs {
+    Grid g;
+    DiffTracer t[2];
+    int ntr;  // 1 or 2 tracers sharing the K_33 matrix
+    double* P_diss;
+    const int32_t *tau, *taup1;
+    const double* K;  // K_iso (iso) or K_gm (skew)
+    const double *Ai_ez, *Ai_nz, *Ai_bx, *Ai_by, *K_11, *K_22, *K_33;
+    const uint8_t *maskT, *maskW;
+    const int32_t* kbot;
+    int skew, energy;
+    double dt_tracer, grav, rho_0;
+};
+
+// ---- launchers (one per translation unit) -----------------------------------------------------
+void launch_iso_pre(cudaStream_t s, const PreArgs& a);
+size_t diffusion_workspace_doubles(int N, int M, int nz, int ntr);
+void launch_iso_diffusion_ws(cudaStream_t s, const DiffArgs& a, double* workspace);
+void launch_solve_implicit(cudaStream_t s, int ncol, int nz, const double* a, const double* b, const double* c,
+                           const double* d, const uint8_t* water, const uint8_t* edge, const double* b_edge,
+                           const double* d_edge, double* out);
+void launch_tdma_zmajor_f64(cudaStream_t s, int nsys, int depth, const double* a, const double* b, const double* c,
+                            const double* d, double* out, double* work);
+void launch_tdma_zmajor_f32(cudaStream_t s, int nsys, int depth, const float* a, const float* b, const float* c,
+                            const float* d, float* out, float* work);
+
+}  // namespace vb

@@ -1,0 +1,395 @@
+// isoneutral_diffusion / isoneutral_skew_diffusion (veros/core/isoneutral/diffusion.py:9-307,
+// dissipation helpers veros/core/diffusion.py:9-62).
+//
+// Two kernels per call:
+//   flux_kernel    one thread per cell: the Griffies triad fluxes on the east / north / top faces
+//                  (diffusion.py:9-113) for one tracer, written to scratch.
+//   update_kernel  one CTA per tile of whole water columns: explicit flux divergence
+//                  (diffusion.py:116-139), tracer update, the implicit K_33 solve
+//                  (diffusion.py:142-169 + utilities.py:38-59 + operators.py:60-77) out of shared
+//                  memory with one thread per column, tendency and dissipation (diffusion.py:196-281).
+//                  With two tracers (temp and salt of one step) the column matrix, which depends on
+//                  K_33 only, is factorised once and applied to both right-hand sides.
+//
+// Arithmetic is "strict": every NumPy ufunc call of the reference is one explicitly rounded
+// operation here, in the reference's order, and the column solve replays dgtsv (tdma_device.cuh),
+// so on identical inputs the outputs are bit-identical to the reference's NumPy backend.  Divisions
+// by grid metrics use correctly rounded reciprocals tabulated once per CTA (strict.cuh).
+#include "common.cuh"
+#include "strict.cuh"
+#include "tdma_device.cuh"
+
+namespace vb {
+
+using strict::add;
+using strict::Divisor;
+using strict::make_divisor;
+using strict::mul;
+using strict::sub;
+
+namespace {
+
+__device__ __forceinline__ double ldt(const double* tr, size_t cell) { return __ldg(tr + cell * 3); }
+
+// ------------------------------------------------------------------------------------------------
+// flux_kernel: grid (ceil(M*nz / blockDim), N); block b of plane i handles flattened cells
+// p in [b*blockDim, (b+1)*blockDim) of that plane (contiguous in memory).
+// Dynamic shared memory: per-level and per-row metric tables (divisor + reciprocal).
+// ------------------------------------------------------------------------------------------------
+template <bool SKEW>
+__global__ void __launch_bounds__(256)
+flux_kernel(const DiffArgs a, const int t, double* __restrict__ flux_east, double* __restrict__ flux_north,
+            double* __restrict__ flux_top) {
+    extern __shared__ double sm[];
+    const int N = a.g.N, M = a.g.M, nz = a.g.nz;
+    const int i = blockIdx.y;
+    const int p0 = blockIdx.x * blockDim.x;
+    const int jlo = p0 / nz;
+    const int jhi = min(M - 1, (p0 + (int)blockDim.x - 1) / nz);
+    const int jr = jhi - jlo + 1;
+
+    Divisor* d4zt = reinterpret_cast<Divisor*>(sm);  // 4*dzt[k]
+    Divisor* dcdxu = d4zt + nz;                      // cost[j]*dxu[i]
+    Divisor* ddyu = dcdxu + jr;                      // dyu[j]
+    Divisor* dcost = ddyu + jr;                      // cost[j]
+    Divisor* d4ytc = dcost + jr;                     // (4*dyt[j])*cost[j]
+    Divisor* d4xt = d4ytc + jr;                      // 4*dxt[i] (one entry)
+    if (threadIdx.x == 0) d4xt[0] = make_divisor(mul(4.0, a.g.dxt[i]));
+    for (int k = threadIdx.x; k < nz; k += blockDim.x) d4zt[k] = make_divisor(mul(4.0, a.g.dzt[k]));
+    for (int q = threadIdx.x; q < jr; q += blockDim.x) {
+        const int j = jlo + q;
+        dcdxu[q] = make_divisor(mul(a.g.cost[j], a.g.dxu[i]));
+        ddyu[q] = make_divisor(a.g.dyu[j]);
+        dcost[q] = make_divisor(a.g.cost[j]);
+        d4ytc[q] = make_divisor(mul(mul(4.0, a.g.dyt[j]), a.g.cost[j]));
+    }
+    __syncthreads();
+
+    const int p = p0 + threadIdx.x;
+    if (p >= M * nz) return;
+    const int j = p / nz;
+    const int k = p - j * nz;
+    const int q = j - jlo;
+    const size_t plane = (size_t)M * nz;
+    const size_t c = (size_t)i * plane + p;
+
+    const bool inE = (i >= 1 && i < N - 2 && j >= 2 && j < M - 2);
+    const bool inN = (i >= 2 && i < N - 2 && j >= 1 && j < M - 2);
+    const bool inT = (i >= 2 && i < N - 2 && j >= 2 && j < M - 2 && k < nz - 1);
+    double fe = 0.0, fn = 0.0, ft = 0.0;
+
+    if (inE || inN || inT) {
+        const int tau = *a.tau;
+        const double* __restrict__ tr = a.t[t].tr + tau;
+        const double* __restrict__ K = a.K;
+        // K1 = K_iso - K_skew, K2 = K_iso + K_skew with the unused one 0.0 (diffusion.py:15-16,180-188)
+        auto K1 = [&](size_t cell) { return SKEW ? sub(0.0, __ldg(K + cell)) : __ldg(K + cell); };
+        const int km = k > 0 ? -1 : 0, kp = k < nz - 1 ? 1 : 0;  // pad_z_edges clamping
+        const double tc = ldt(tr, c), tcm = ldt(tr, c + km), tcp = ldt(tr, c + kp);
+        const double dz0_c = sub(tc, tcm), dz1_c = sub(tcp, tc);
+
+        if (inE) {  // diffusion.py:25-47
+            const size_t ce = c + plane;
+            const double te = ldt(tr, ce), tem = ldt(tr, ce + km), tep = ldt(tr, ce + kp);
+            double diffloc;
+            if (k > 0)
+                diffloc = mul(0.25, add(add(add(K1(c), K1(c - 1)), K1(ce)), K1(ce - 1)));
+            else
+                diffloc = mul(0.5, add(K1(c), K1(ce)));
+            const double2 A0 = __ldg(reinterpret_cast<const double2*>(a.Ai_ez + c * 4));      // ip=0: kr=0,1
+            const double2 A1 = __ldg(reinterpret_cast<const double2*>(a.Ai_ez + c * 4) + 1);  // ip=1
+            double sumz = add(0.0, mul(mul(diffloc, A0.x), dz0_c));
+            sumz = add(sumz, mul(mul(diffloc, A1.x), sub(te, tem)));
+            sumz = add(sumz, mul(mul(diffloc, A0.y), dz1_c));
+            sumz = add(sumz, mul(mul(diffloc, A1.y), sub(tep, te)));
+            fe = add(strict::div(sumz, d4zt[k]), mul(strict::div(sub(te, tc), dcdxu[q]), __ldg(a.K_11 + c)));
+        }
+        if (inN) {  // diffusion.py:52-77
+            const size_t cn = c + nz;
+            const double tn = ldt(tr, cn), tnm = ldt(tr, cn + km), tnp = ldt(tr, cn + kp);
+            double diffloc;
+            if (k > 0)
+                diffloc = mul(0.25, add(add(add(K1(c), K1(c - 1)), K1(cn)), K1(cn - 1)));
+            else
+                diffloc = mul(0.5, add(K1(c), K1(cn)));
+            const double2 A0 = __ldg(reinterpret_cast<const double2*>(a.Ai_nz + c * 4));
+            const double2 A1 = __ldg(reinterpret_cast<const double2*>(a.Ai_nz + c * 4) + 1);
+            double sumz = add(0.0, mul(mul(diffloc, A0.x), dz0_c));
+            sumz = add(sumz, mul(mul(diffloc, A1.x), sub(tn, tnm)));
+            sumz = add(sumz, mul(mul(diffloc, A0.y), dz1_c));
+            sumz = add(sumz, mul(mul(diffloc, A1.y), sub(tnp, tn)));
+            fn = mul(__ldg(a.g.cosu + j),
+                     add(strict::div(sumz, d4zt[k]), mul(strict::div(sub(tn, tc), ddyu[q]), __ldg(a.K_22 + c))));
+        }
+        if (inT) {  // diffusion.py:85-111 (k < nz-1 here, so level k+1 exists)
+            const size_t ce = c + plane, cw = c - plane, cn = c + nz, cs = c - nz;
+            const double diffloc = SKEW ? add(0.0, __ldg(K + c)) : __ldg(K + c);
+            const double2 X0 = __ldg(reinterpret_cast<const double2*>(a.Ai_bx + c * 4));
+            const double2 X1 = __ldg(reinterpret_cast<const double2*>(a.Ai_bx + c * 4) + 1);
+            const double2 Y0 = __ldg(reinterpret_cast<const double2*>(a.Ai_by + c * 4));
+            const double2 Y1 = __ldg(reinterpret_cast<const double2*>(a.Ai_by + c * 4) + 1);
+            const double tu = tcp;  // (i,j,k+1)
+            const double te = ldt(tr, ce), teu = ldt(tr, ce + 1), tw = ldt(tr, cw), twu = ldt(tr, cw + 1);
+            const double tn = ldt(tr, cn), tnu = ldt(tr, cn + 1), ts = ldt(tr, cs), tsu = ldt(tr, cs + 1);
+            // ip outer, kr inner
+            double sumx = add(0.0, mul(strict::div(mul(diffloc, X0.x), dcost[q]), sub(tc, tw)));
+            sumx = add(sumx, mul(strict::div(mul(diffloc, X0.y), dcost[q]), sub(tu, twu)));
+            sumx = add(sumx, mul(strict::div(mul(diffloc, X1.x), dcost[q]), sub(te, tc)));
+            sumx = add(sumx, mul(strict::div(mul(diffloc, X1.y), dcost[q]), sub(teu, tu)));
+            const double cu0 = __ldg(a.g.cosu + j - 1), cu1 = __ldg(a.g.cosu + j);
+            double sumy = add(0.0, mul(mul(mul(diffloc, Y0.x), cu0), sub(tc, ts)));
+            sumy = add(sumy, mul(mul(mul(diffloc, Y0.y), cu0), sub(tu, tsu)));
+            sumy = add(sumy, mul(mul(mul(diffloc, Y1.x), cu1), sub(tn, tc)));
+            sumy = add(sumy, mul(mul(mul(diffloc, Y1.y), cu1), sub(tnu, tu)));
+            ft = add(strict::div(sumx, d4xt[0]), strict::div(sumy, d4ytc[q]));
+        }
+    }
+    flux_east[c] = fe;
+    flux_north[c] = fn;
+    flux_top[c] = ft;
+}
+
+// ------------------------------------------------------------------------------------------------
+// update_kernel: grid (tiles over j in [1, M-1), planes i in [1, N-1)).  A tile is `cols` whole
+// columns of one x-plane = one contiguous piece of every (N,M,nz) array.
+// Shared memory (doubles, column pitch odd): L, D, U, R[NTR], DISS[NTR] (ENERGY), metric tables.
+// ------------------------------------------------------------------------------------------------
+struct Scratch {
+    const double *fe[2], *fn[2], *ft[2];
+};
+
+template <int NTR, bool SKEW, bool ENERGY>
+__global__ void __launch_bounds__(256)
+update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch, const double fac_diss,
+              const double gr) {
+    extern __shared__ double sm[];
+    const int N = a.g.N, M = a.g.M, nz = a.g.nz;
+    const int i = 1 + blockIdx.y;
+    const int j0 = 1 + blockIdx.x * cols;
+    const int ncols = min(cols, (M - 1) - j0);
+    const int tile = cols * pitch;
+
+    double* L = sm;
+    double* D = L + tile;
+    double* U = D + tile;
+    double* R[2] = {U + tile, U + tile * 2};
+    double* DISS[2] = {U + tile * (1 + NTR), U + tile * (2 + NTR)};
+    double* tab = U + tile * (1 + NTR + (ENERGY ? NTR : 0));
+    Divisor* ddzt = reinterpret_cast<Divisor*>(tab);  // dzt[k]
+    Divisor* ddzw = ddzt + nz;                        // dzw[k]
+    double* dt_dzw = reinterpret_cast<double*>(ddzw + nz);  // dt_tracer / dzw[k]
+    Divisor* dcdxt = reinterpret_cast<Divisor*>(dt_dzw + nz);  // cost[j]*dxt[i]
+    Divisor* dcdyt = dcdxt + cols;                              // cost[j]*dyt[j]
+    int* ksv = reinterpret_cast<int*>(dcdyt + cols);            // kbot-1 per column
+
+    const double dt = a.dt_tracer;
+    for (int k = threadIdx.x; k < nz; k += blockDim.x) {
+        ddzt[k] = make_divisor(a.g.dzt[k]);
+        ddzw[k] = make_divisor(a.g.dzw[k]);
+        dt_dzw[k] = strict::div(dt, a.g.dzw[k]);
+    }
+    for (int q = threadIdx.x; q < ncols; q += blockDim.x) {
+        const int j = j0 + q;
+        dcdxt[q] = make_divisor(mul(a.g.cost[j], a.g.dxt[i]));
+        dcdyt[q] = make_divisor(mul(a.g.cost[j], a.g.dyt[j]));
+        ksv[q] = a.kbot[i * M + j] - 1;
+    }
+    __syncthreads();
+
+    const Divisor ddt = make_divisor(dt);
+    const int tau = *a.tau, taup1 = *a.taup1;
+    const size_t plane = (size_t)M * nz;
+    const size_t base = (size_t)i * plane + (size_t)j0 * nz;
+    const int ncells = ncols * nz;
+    const bool i_int = (i >= 2 && i < N - 2);
+
+    // ---- phase B: explicit part, rhs, matrix, dissipation on T points ---------------------------
+    for (int idx = threadIdx.x; idx < ncells; idx += blockDim.x) {
+        const int q = idx / nz, k = idx - q * nz;
+        const int j = j0 + q;
+        const size_t c = base + idx;
+        const int s = q * pitch + k;
+        const bool interior = i_int && j >= 2 && j < M - 2;
+#pragma unroll
+        for (int t = 0; t < NTR; ++t) {
+            const double fe_c = __ldg(f.fe[t] + c), fe_w = __ldg(f.fe[t] + c - plane);
+            const double fn_c = __ldg(f.fn[t] + c), fn_s = __ldg(f.fn[t] + c - nz);
+            if (interior) {
+                const double mT = (double)a.maskT[c];
+                const double ft_c = __ldg(f.ft[t] + c);
+                double e = mul(mT, add(strict::div(sub(fe_c, fe_w), dcdxt[q]), strict::div(sub(fn_c, fn_s), dcdyt[q])));
+                if (k == 0)
+                    e = add(e, strict::div(mul(mT, ft_c), ddzt[0]));
+                else
+                    e = add(e, strict::div(mul(mT, sub(ft_c, __ldg(f.ft[t] + c - 1))), ddzt[k]));
+                a.t[t].dtracer[c] = add(a.t[t].dtracer[c], e);            // diffusion.py:196
+                const double v = add(a.t[t].tr[c * 3 + taup1], mul(dt, e));  // diffusion.py:197
+                a.t[t].tr[c * 3 + taup1] = v;
+                if (!SKEW) R[t][s] = v;
+            }
+            if (ENERGY) {  // compute_dissipation, veros/core/diffusion.py:15-35 (on [1:-1, 1:-1])
+                const double* __restrict__ X = a.t[t].int_drhodX + tau;
+                const double xc = ldt(X, c);
+                const double gx = add(mul(sub(ldt(X, c + plane), xc), fe_c), mul(sub(xc, ldt(X, c - plane)), fe_w));
+                const double gy = add(mul(sub(ldt(X, c + nz), xc), fn_c), mul(sub(xc, ldt(X, c - nz)), fn_s));
+                DISS[t][s] = add(strict::div(mul(fac_diss, gx), dcdxt[q]), strict::div(mul(fac_diss, gy), dcdyt[q]));
+            }
+        }
+        if (!SKEW && interior) {  // _calc_implicit_part, diffusion.py:149-164
+            const int ks = ksv[q];
+            const double del = (k < nz - 1) ? mul(dt_dzw[k], __ldg(a.K_33 + c)) : 0.0;
+            const double delm = (k > 0) ? mul(dt_dzw[k - 1], __ldg(a.K_33 + c - 1)) : 0.0;
+            double b;
+            if (k == ks)
+                b = add(1.0, strict::div(del, ddzt[k]));  // b_tri_edge
+            else if (k == nz - 1)
+                b = add(1.0, strict::div(delm, ddzt[k]));
+            else
+                b = add(1.0, strict::div(add(del, delm), ddzt[k]));
+            D[s] = b;
+            U[s] = (k < nz - 1) ? strict::div(-del, ddzt[k]) : 0.0;
+            if (k > 0) L[s - 1] = (k > ks) ? strict::div(-delm, ddzt[k]) : 0.0;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: one thread per water column, dgtsv on both right-hand sides -------------------
+    if (!SKEW && i_int) {
+        for (int q = threadIdx.x; q < ncols; q += blockDim.x) {
+            const int j = j0 + q;
+            const int ks = ksv[q];
+            if (j >= 2 && j < M - 2 && ks >= 0) {
+                const int o = q * pitch;
+                dgtsv_column<NTR>(ks, nz, 1, L + o, D + o, U + o, R[0] + o, R[NTR - 1] + o);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase D: tracer, tendency, dissipation -------------------------------------------------
+    for (int idx = threadIdx.x; idx < ncells; idx += blockDim.x) {
+        const int q = idx / nz, k = idx - q * nz;
+        const int j = j0 + q;
+        const size_t c = base + idx;
+        const int s = q * pitch + k;
+        const bool interior = i_int && j >= 2 && j < M - 2;
+        const int ks = ksv[q];
+        const bool land = ks >= 0;
+        double P = 0.0;
+        if (ENERGY) P = a.P_diss[c];
+#pragma unroll
+        for (int t = 0; t < NTR; ++t) {
+            if (!SKEW && interior && land && k >= ks) {  // where(water_mask, sol, tr); diffusion.py:168,203-204
+                const double old = a.t[t].tr[c * 3 + taup1];
+                const double nw = R[t][s];
+                a.t[t].dtracer[c] = add(a.t[t].dtracer[c], strict::div(sub(nw, old), ddt));
+                a.t[t].tr[c * 3 + taup1] = nw;
+            }
+            if (ENERGY) {
+                // dissipation_on_wgrid, veros/core/diffusion.py:41-62
+                const double dk = DISS[t][s];
+                double dw;
+                if (k < nz - 1) {
+                    const double m = mul(0.5, add(dk, DISS[t][s + 1]));
+                    const double edge = (land && k == ks) ? 1.0 : 0.0, water = (land && k > ks) ? 1.0 : 0.0;
+                    const double dzw_pad = a.g.dzw[k > 0 ? k - 1 : 0];
+                    dw = add(mul(add(m, mul(0.5, strict::div(mul(dk, dzw_pad), ddzw[k]))), edge), mul(m, water));
+                } else {
+                    dw = mul(dk, land ? 1.0 : 0.0);
+                }
+                P = add(P, dw);  // diffusion.py:246-249
+                if (interior && k < nz - 1) {  // diffusion.py:254-279
+                    const double* __restrict__ X = a.t[t].int_drhodX + tau;
+                    const double fxa = strict::div(add(-ldt(X, c + 1), ldt(X, c)), ddzw[k]);
+                    const double mW = (double)a.maskW[c];
+                    const double ft_c = __ldg(f.ft[t] + c);
+                    double v;
+                    if (SKEW) {
+                        v = mul(mul(mul(gr, fxa), ft_c), mW);
+                    } else {
+                        // tr[taup1] after the update: R holds it for every interior cell of the tile
+                        const double dtr = sub(R[t][s + 1], R[t][s]);
+                        v = mul(mul(gr, fxa),
+                                add(mul(ft_c, mW), mul(strict::div(mul(__ldg(a.K_33 + c), dtr), ddzw[k]), mW)));
+                    }
+                    P = add(P, v);
+                }
+            }
+        }
+        if (ENERGY) a.P_diss[c] = P;
+    }
+}
+
+template <int NTR, bool SKEW, bool ENERGY>
+void launch_update(cudaStream_t s, const DiffArgs& a, const Scratch& f) {
+    const int M = a.g.M, N = a.g.N, nz = a.g.nz;
+    const int pitch = nz | 1;
+    const int narr = 3 + NTR + (ENERGY ? NTR : 0);
+    int cols = (56 * 1024) / (narr * 8 * pitch);
+    cols = max(1, min(cols, M - 2));
+    const int want_tiles = 2 * 148;  // small grids: spread over the SMs
+    const int rows = N - 2;
+    if (((M - 2 + cols - 1) / cols) * rows < want_tiles) {
+        const int per_row = (want_tiles + rows - 1) / rows;
+        cols = max(1, (M - 2 + per_row - 1) / per_row);
+    }
+    const size_t smem = (size_t)narr * 8 * cols * pitch + (size_t)nz * (2 * sizeof(Divisor) + 8) +
+                        (size_t)cols * (2 * sizeof(Divisor) + sizeof(int)) + 16;
+    auto kern = update_kernel<NTR, SKEW, ENERGY>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+    }
+    dim3 grid((M - 2 + cols - 1) / cols, N - 2);
+    const double fac_diss = 0.5 * a.grav / a.rho_0;  // diffusion.py (core) :19-21, Python float arithmetic
+    const double gr = -a.grav / a.rho_0;             // isoneutral/diffusion.py:259,268
+    kern<<<grid, 256, smem, s>>>(a, f, cols, pitch, fac_diss, gr);
+    count_launch();
+    check_launch("update_kernel");
+}
+
+}  // namespace
+
+// workspace layout (doubles): per tracer flux_east, flux_north, flux_top, each N*M*nz
+size_t diffusion_workspace_doubles(int N, int M, int nz, int ntr) { return (size_t)3 * ntr * N * M * nz; }
+
+void launch_iso_diffusion_ws(cudaStream_t s, const DiffArgs& a, double* ws) {
+    const int N = a.g.N, M = a.g.M, nz = a.g.nz;
+    if (N < 5 || M < 5 || nz < 2) return;
+    const size_t n3 = (size_t)N * M * nz;
+    Scratch f;
+    for (int t = 0; t < a.ntr; ++t) {
+        double* fe = ws + (size_t)(3 * t) * n3;
+        double* fn = fe + n3;
+        double* ft = fn + n3;
+        f.fe[t] = fe;
+        f.fn[t] = fn;
+        f.ft[t] = ft;
+        const int block = 256;
+        dim3 grid((M * nz + block - 1) / block, N);
+        const int jr = block / nz + 2;
+        const size_t smem = sizeof(Divisor) * ((size_t)nz + 4 * jr + 1);
+        if (a.skew)
+            flux_kernel<true><<<grid, block, smem, s>>>(a, t, fe, fn, ft);
+        else
+            flux_kernel<false><<<grid, block, smem, s>>>(a, t, fe, fn, ft);
+        count_launch();
+        if (!check_launch("flux_kernel")) return;
+    }
+    if (a.ntr == 1) {
+        f.fe[1] = f.fe[0]; f.fn[1] = f.fn[0]; f.ft[1] = f.ft[0];
+    }
+#define VB_DISPATCH(NTR)                                                                   \
+    if (a.skew) {                                                                          \
+        if (a.energy) launch_update<NTR, true, true>(s, a, f);                             \
+        else launch_update<NTR, true, false>(s, a, f);                                     \
+    } else {                                                                               \
+        if (a.energy) launch_update<NTR, false, true>(s, a, f);                            \
+        else launch_update<NTR, false, false>(s, a, f);                                    \
+    }
+    if (a.ntr == 2) { VB_DISPATCH(2) } else { VB_DISPATCH(1) }
+#undef VB_DISPATCH
+}
+
+}  // namespace vb

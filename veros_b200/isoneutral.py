@@ -1,0 +1,100 @@
+"""Host side of the isoneutral mixing step: same names, arguments and return conventions as
+``veros.core.isoneutral`` (veros/core/isoneutral/__init__.py), executing hand-written sm_100a
+kernels through the XLA-custom-call C ABI of libveros_b200.so.
+
+    isoneutral_diffusion_pre(state) -> KernelOutput(Ai_ez, Ai_nz, Ai_bx, Ai_by, K_11, K_22, K_33)
+        veros/core/isoneutral/isoneutral.py:18-229
+    isoneutral_diffusion(state, tr, istemp) -> None (updates temp|salt, dtemp_iso|dsalt_iso, P_diss_iso)
+        veros/core/isoneutral/diffusion.py:286-295
+    isoneutral_skew_diffusion(state, tr, istemp) -> None
+        veros/core/isoneutral/diffusion.py:298-307
+    isoneutral_step(state) -> None: the three calls of veros/core/thermodynamics.py:430-432 as one op
+
+All work is enqueued on the current CUDA stream of ``state.device``; nothing synchronises.
+"""
+import torch
+
+from . import _lib
+from .state import KernelOutput
+
+_PRE_OUT = ("Ai_ez", "Ai_nz", "Ai_bx", "Ai_by", "K_11", "K_22", "K_33")
+_METRICS = ("dxt", "dxu", "dyt", "dyu", "cost", "cosu", "dzt", "dzw")
+
+
+def _descriptor(state, flags=0):
+    st = state.settings
+    return _lib.IsoDescriptor(
+        nx_tot=st.nx + 4, ny_tot=st.ny + 4, nz=st.nz, eq_of_state_type=st.eq_of_state_type,
+        enable_conserve_energy=int(st.enable_conserve_energy), flags=flags,
+        K_iso_steep=st.K_iso_steep, iso_slopec=st.iso_slopec, iso_dslope=st.iso_dslope,
+        dt_tracer=st.dt_tracer, grav=st.grav, rho_0=st.rho_0)
+
+
+def _stream(state):
+    return torch.cuda.current_stream(state.device).cuda_stream
+
+
+def _ptrs(tensors):
+    return [int(t.data_ptr()) for t in tensors]
+
+
+def isoneutral_diffusion_pre(state):
+    """Isopycnal slopes and mixing tensor; returns the seven updated arrays (updated in place)."""
+    vs = state.variables
+    desc = _descriptor(state)
+    opaque = bytes(desc)
+    ws = state.workspace(_lib.lib().veros_b200_iso_pre_workspace_bytes(opaque, len(opaque)))
+    inout = [getattr(vs, n) for n in _PRE_OUT]
+    operands = [vs.temp, vs.salt, vs.tau, vs.K_iso, vs.maskT, vs.maskU, vs.maskV, vs.maskW]
+    operands += [getattr(vs, n) for n in _METRICS] + [vs.zt] + inout
+    _lib.call("veros_b200_iso_pre_f64", _ptrs(operands + inout + [ws]), desc, _stream(state))
+    return KernelOutput(**dict(zip(_PRE_OUT, inout)))
+
+
+def _diffusion(state, tr, istemp, skew):
+    vs, st = state.variables, state.settings
+    if tr is not vs.temp and tr is not vs.salt:
+        if tr.data_ptr() not in (vs.temp.data_ptr(), vs.salt.data_ptr()):
+            raise ValueError("tr must be state.variables.temp or state.variables.salt")
+    energy = st.enable_conserve_energy
+    dtracer = vs.dtemp_iso if istemp else vs.dsalt_iso
+    dummy = state.dummy()
+    if energy:
+        P = vs.P_diss_skew if skew else vs.P_diss_iso
+        X = vs.int_drhodT if istemp else vs.int_drhodS
+    else:
+        P = X = dummy
+    K = vs.K_gm if skew else vs.K_iso
+    desc = _descriptor(state, _lib.FLAG_SKEW if skew else 0)
+    opaque = bytes(desc)
+    ws = state.workspace(_lib.lib().veros_b200_iso_diffusion_workspace_bytes(opaque, len(opaque)))
+    operands = [tr, dtracer, P, vs.tau, vs.taup1, K, vs.Ai_ez, vs.Ai_nz, vs.Ai_bx, vs.Ai_by, vs.K_11, vs.K_22,
+                vs.K_33, vs.maskT, vs.maskW, vs.kbot] + [getattr(vs, n) for n in _METRICS] + [X]
+    results = [tr, dtracer, P, ws]
+    _lib.call("veros_b200_iso_diffusion_f64", _ptrs(operands + results), desc, _stream(state))
+
+
+def isoneutral_diffusion(state, tr, istemp):
+    """Isopycnal diffusion of one tracer incl. the implicit K_33 column solve (in place on state)."""
+    _diffusion(state, tr, istemp, skew=False)
+
+
+def isoneutral_skew_diffusion(state, tr, istemp):
+    """GM skew diffusion of one tracer (in place on state)."""
+    _diffusion(state, tr, istemp, skew=True)
+
+
+def isoneutral_step(state):
+    """pre + isoneutral_diffusion(temp) + isoneutral_diffusion(salt) (thermodynamics.py:430-432)."""
+    vs, st = state.variables, state.settings
+    energy = st.enable_conserve_energy
+    dummy = state.dummy()
+    desc = _descriptor(state)
+    opaque = bytes(desc)
+    ws = state.workspace(_lib.lib().veros_b200_iso_step_workspace_bytes(opaque, len(opaque)))
+    inout = [vs.temp, vs.salt, vs.dtemp_iso, vs.dsalt_iso, vs.P_diss_iso if energy else dummy]
+    inout += [getattr(vs, n) for n in _PRE_OUT]
+    operands = inout + [vs.tau, vs.taup1, vs.K_iso, vs.maskT, vs.maskU, vs.maskV, vs.maskW, vs.kbot]
+    operands += [getattr(vs, n) for n in _METRICS] + [vs.zt]
+    operands += [vs.int_drhodT if energy else dummy, vs.int_drhodS if energy else dummy]
+    _lib.call("veros_b200_iso_step_f64", _ptrs(operands + inout + [ws]), desc, _stream(state))

@@ -1,0 +1,129 @@
+"""Device-resident state for the isoneutral path.
+
+Mirrors the two containers the reference's kernels read (veros/state.py: ``state.variables`` and
+``state.settings``) with exactly the variable / setting names of veros/variables.py and
+veros/settings.py that the hot path touches, so host code reads like the reference's:
+
+    vs = state.variables
+    vs.update(isoneutral.isoneutral_diffusion_pre(state))
+
+Arrays are torch CUDA tensors used purely as device buffers (dtype / shape / data_ptr); no torch
+arithmetic is ever applied to them.
+"""
+from collections import namedtuple
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+F64_3D = ("K_iso", "K_gm", "K_11", "K_22", "K_33", "dtemp_iso", "dsalt_iso", "P_diss_iso", "P_diss_skew")
+F64_4D = ("temp", "salt", "int_drhodT", "int_drhodS")
+F64_5D = ("Ai_ez", "Ai_nz", "Ai_bx", "Ai_by")
+MASKS = ("maskT", "maskU", "maskV", "maskW")
+METRICS_X = ("dxt", "dxu")
+METRICS_Y = ("dyt", "dyu", "cost", "cosu")
+METRICS_Z = ("dzt", "dzw", "zt")
+SETTINGS = ("eq_of_state_type", "enable_conserve_energy", "K_iso_steep", "iso_slopec", "iso_dslope",
+            "dt_tracer", "grav", "rho_0")
+OPTIONAL = ("K_gm", "P_diss_skew", "int_drhodT", "int_drhodS", "P_diss_iso")
+
+
+def KernelOutput(**kwargs):
+    """Same factory as veros.state.KernelOutput (veros/state.py:16-20)."""
+    return namedtuple("KernelOutput", list(kwargs.keys()))(*kwargs.values())
+
+
+class Variables(SimpleNamespace):
+    def update(self, out):
+        """vs.update(KernelOutput) as in veros/state.py."""
+        for k, v in out._asdict().items():
+            setattr(self, k, v)
+
+
+class IsoState:
+    """``state.variables`` / ``state.settings`` for the isoneutral path, on one GPU."""
+
+    def __init__(self, variables, settings, device):
+        self.variables = variables
+        self.settings = settings
+        self.device = device
+        self._workspace = None
+        self._dummy = torch.zeros(8, dtype=torch.float64, device=device)
+
+    # ---- construction --------------------------------------------------------------------------
+    @classmethod
+    def from_numpy(cls, st, device="cuda"):
+        """`st`: dict keyed by reference variable / setting names (see tests/helpers.py)."""
+        device = torch.device(device)
+        N, M, nz = st["K_iso"].shape
+        vs = Variables()
+
+        def put(name, arr, dtype):
+            arr = np.ascontiguousarray(arr, dtype=dtype)
+            setattr(vs, name, torch.from_numpy(arr).to(device))
+
+        for name in F64_3D + F64_4D + F64_5D + METRICS_X + METRICS_Y + METRICS_Z:
+            if name in st:
+                put(name, st[name], np.float64)
+            elif name not in OPTIONAL:
+                raise KeyError(name)
+        for name in MASKS:
+            put(name, np.asarray(st[name]).astype(np.uint8), np.uint8)
+        put("kbot", st["kbot"], np.int32)
+        for name in ("tau", "taup1"):
+            put(name, np.array([int(st[name])]), np.int32)
+        settings = SimpleNamespace(**{k: st[k] for k in SETTINGS})
+        settings.eq_of_state_type = int(settings.eq_of_state_type)
+        settings.enable_conserve_energy = bool(settings.enable_conserve_energy)
+        for k in SETTINGS[2:]:
+            setattr(settings, k, float(getattr(settings, k)))
+        settings.nx, settings.ny, settings.nz = N - 4, M - 4, nz
+        obj = cls(vs, settings, device)
+        obj.validate()
+        return obj
+
+    def validate(self):
+        vs, st = self.variables, self.settings
+        N, M, nz = st.nx + 4, st.ny + 4, st.nz
+        shapes = {**{n: (N, M, nz) for n in F64_3D + MASKS}, **{n: (N, M, nz, 3) for n in F64_4D},
+                  **{n: (N, M, nz, 2, 2) for n in F64_5D}, **{n: (N,) for n in METRICS_X},
+                  **{n: (M,) for n in METRICS_Y}, **{n: (nz,) for n in METRICS_Z}, "kbot": (N, M),
+                  "tau": (1,), "taup1": (1,)}
+        for name, shape in shapes.items():
+            t = getattr(vs, name, None)
+            if t is None:
+                if name in OPTIONAL:
+                    continue
+                raise ValueError(f"state is missing variable {name}")
+            if tuple(t.shape) != shape:
+                raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {shape}")
+            want = torch.uint8 if name in MASKS else torch.int32 if name in ("kbot", "tau", "taup1") else torch.float64
+            if t.dtype != want:
+                raise TypeError(f"{name} has dtype {t.dtype}, expected {want}")
+            if not t.is_contiguous():
+                raise ValueError(f"{name} must be C-contiguous")
+        if st.enable_conserve_energy:
+            for name in ("int_drhodT", "int_drhodS", "P_diss_iso"):
+                if getattr(vs, name, None) is None:
+                    raise ValueError(f"enable_conserve_energy needs variable {name}")
+        if not 1 <= st.eq_of_state_type <= 5:
+            raise ValueError("unknown equation of state")
+
+    # ---- helpers --------------------------------------------------------------------------------
+    def to_numpy(self, names=None):
+        vs = self.variables
+        names = names or [n for n in vars(vs)]
+        out = {}
+        for n in names:
+            t = getattr(vs, n)
+            out[n] = t.cpu().numpy()
+        return out
+
+    def workspace(self, nbytes):
+        n = max(8, (int(nbytes) + 7) // 8)
+        if self._workspace is None or self._workspace.numel() < n:
+            self._workspace = torch.empty(n, dtype=torch.float64, device=self.device)
+        return self._workspace
+
+    def dummy(self):
+        return self._dummy
