@@ -1,7 +1,8 @@
 /*
  * oracle/iso_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
- * Scalar, single-threaded CPU restatement (plain C, IEEE double, no FMA contraction) of the
+ * Scalar CPU restatement (plain C, IEEE double, no FMA contraction; optional OpenMP over x-planes,
+ * which does not change any result bit) of the
  * reference's isoneutral-mixing hot path.  It exists only to CHECK the CUDA kernels:
  * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load it.  The product path (veros_b200/) never imports, links or calls anything in oracle/.
@@ -180,6 +181,7 @@ void oracle_iso_pre(const oracle_params *P, const double *temp, const double *sa
     double *dTdz = calloc(n3, 8), *dSdz = calloc(n3, 8);
     (void)dxt;
 
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < N; i++)
         for (int j = 0; j < M; j++)
             for (int k = 0; k < nz; k++) {
@@ -206,6 +208,7 @@ void oracle_iso_pre(const oracle_params *P, const double *temp, const double *sa
             }
 
     /* east face: Ai_ez, K_11  (:100-132) */
+#pragma omp parallel for schedule(static)
     for (int i = 1; i < N - 2; i++)
         for (int j = 2; j < M - 2; j++)
             for (int k = 0; k < nz; k++) {
@@ -233,6 +236,7 @@ void oracle_iso_pre(const oracle_params *P, const double *temp, const double *sa
             }
 
     /* north face: Ai_nz, K_22  (:137-168) */
+#pragma omp parallel for schedule(static)
     for (int i = 2; i < N - 2; i++)
         for (int j = 1; j < M - 2; j++)
             for (int k = 0; k < nz; k++) {
@@ -260,6 +264,7 @@ void oracle_iso_pre(const oracle_params *P, const double *temp, const double *sa
             }
 
     /* top face: Ai_bx, Ai_by, K_33  (:173-225) */
+#pragma omp parallel for schedule(static)
     for (int i = 2; i < N - 2; i++)
         for (int j = 2; j < M - 2; j++)
             for (int k = 0; k < nz - 1; k++) {
@@ -370,8 +375,11 @@ static void solve_column(int nz, const double *a, const double *b, const double 
 void oracle_solve_implicit(int64_t ncol, int32_t nz, const double *a, const double *b, const double *c,
                            const double *d, const uint8_t *water, const uint8_t *edge, const double *b_edge,
                            const double *d_edge, double *out, int32_t mode) {
+#pragma omp parallel
+    {
     double *bb = malloc(8 * (size_t)nz), *dd = malloc(8 * (size_t)nz);
     double *w1 = malloc(8 * (size_t)nz), *w2 = malloc(8 * (size_t)nz);
+#pragma omp for schedule(static)
     for (int64_t col = 0; col < ncol; col++) {
         size_t o = (size_t)col * nz;
         for (int k = 0; k < nz; k++) {
@@ -381,7 +389,18 @@ void oracle_solve_implicit(int64_t ncol, int32_t nz, const double *a, const doub
         solve_column(nz, a + o, bb, c + o, dd, water + o, edge + o, out + o, w1, w2, mode);
     }
     free(bb); free(dd); free(w1); free(w2);
+    }
 }
+
+/* number of OpenMP threads the loops above will use (1 when built without -fopenmp) */
+#ifdef _OPENMP
+#include <omp.h>
+int oracle_num_threads(void) { return omp_get_max_threads(); }
+void oracle_set_num_threads(int n) { omp_set_num_threads(n); }
+#else
+int oracle_num_threads(void) { return 1; }
+void oracle_set_num_threads(int n) { (void)n; }
+#endif
 
 /* ------------------------------------------------------------------------------------------
  * isoneutral_diffusion / isoneutral_skew_diffusion for one tracer
@@ -413,6 +432,7 @@ void oracle_iso_diffusion(const oracle_params *P, int32_t iso, double *tr, doubl
 #define TRP(i, j, kk) tr[TIDX(i, j, (kk) < 0 ? 0 : ((kk) > nz - 1 ? nz - 1 : (kk)), tau)]
 #define TR(i, j, k) tr[TIDX(i, j, k, tau)]
 
+#pragma omp parallel for schedule(static)
     for (int i = 1; i < N - 2; i++) /* east flux (:25-47) */
         for (int j = 2; j < M - 2; j++)
             for (int k = 0; k < nz; k++) {
@@ -426,6 +446,7 @@ void oracle_iso_diffusion(const oracle_params *P, int32_t iso, double *tr, doubl
                 flux_east[IDX(i, j, k)] =
                     sumz / (4.0 * dzt[k]) + (TR(i + 1, j, k) - TR(i, j, k)) / (cost[j] * dxu[i]) * K_11[IDX(i, j, k)];
             }
+#pragma omp parallel for schedule(static)
     for (int i = 2; i < N - 2; i++) /* north flux (:52-77) */
         for (int j = 1; j < M - 2; j++)
             for (int k = 0; k < nz; k++) {
@@ -439,6 +460,7 @@ void oracle_iso_diffusion(const oracle_params *P, int32_t iso, double *tr, doubl
                 flux_north[IDX(i, j, k)] =
                     cosu[j] * (sumz / (4.0 * dzt[k]) + (TR(i, j + 1, k) - TR(i, j, k)) / dyu[j] * K_22[IDX(i, j, k)]);
             }
+#pragma omp parallel for schedule(static)
     for (int i = 2; i < N - 2; i++) /* top flux (:85-111) */
         for (int j = 2; j < M - 2; j++)
             for (int k = 0; k < nz - 1; k++) {
@@ -460,6 +482,7 @@ void oracle_iso_diffusion(const oracle_params *P, int32_t iso, double *tr, doubl
 #undef TR
 
     /* explicit part (:116-139), dtracer += dtr, tr[taup1] += dt*dtr (:195-197) */
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < N; i++)
         for (int j = 0; j < M; j++)
             for (int k = 0; k < nz; k++) {
@@ -479,9 +502,12 @@ void oracle_iso_diffusion(const oracle_params *P, int32_t iso, double *tr, doubl
 
     /* implicit part (:142-169, :201-205) */
     if (iso) {
+#pragma omp parallel
+        {
         double *a = calloc(nz, 8), *b = calloc(nz, 8), *c = calloc(nz, 8), *d = calloc(nz, 8), *delta = calloc(nz, 8);
         double *be = calloc(nz, 8), *x = calloc(nz, 8), *w1 = calloc(nz, 8), *w2 = calloc(nz, 8);
         uint8_t *water = calloc(nz, 1), *edge = calloc(nz, 1);
+#pragma omp for schedule(static)
         for (int i = 2; i < N - 2; i++)
             for (int j = 2; j < M - 2; j++) {
                 int ks = kbot[i * M + j] - 1;
@@ -510,6 +536,7 @@ void oracle_iso_diffusion(const oracle_params *P, int32_t iso, double *tr, doubl
                 }
             }
         free(a); free(b); free(c); free(d); free(delta); free(be); free(x); free(w1); free(w2); free(water); free(edge);
+        }
     }
 
     /* dissipation (:234-281; veros/core/diffusion.py:9-62) */
@@ -517,6 +544,7 @@ void oracle_iso_diffusion(const oracle_params *P, int32_t iso, double *tr, doubl
         double *diss = calloc(n3, 8);
         const double fac = 0.5 * P->grav / P->rho_0;
 #define X(i, j, k) int_drhodX[TIDX(i, j, k, tau)]
+#pragma omp parallel for schedule(static)
         for (int i = 1; i < N - 1; i++)
             for (int j = 1; j < M - 1; j++)
                 for (int k = 0; k < nz; k++)
@@ -525,6 +553,7 @@ void oracle_iso_diffusion(const oracle_params *P, int32_t iso, double *tr, doubl
                                (X(i, j, k) - X(i - 1, j, k)) * flux_east[IDX(i - 1, j, k)]) / (dxt[i] * cost[j]) +
                         fac * ((X(i, j + 1, k) - X(i, j, k)) * flux_north[IDX(i, j, k)] +
                                (X(i, j, k) - X(i, j - 1, k)) * flux_north[IDX(i, j - 1, k)]) / (dyt[j] * cost[j]);
+#pragma omp parallel for schedule(static)
         for (int i = 0; i < N; i++)
             for (int j = 0; j < M; j++) {
                 int ks = kbot[i * M + j] - 1;
@@ -543,6 +572,7 @@ void oracle_iso_diffusion(const oracle_params *P, int32_t iso, double *tr, doubl
                 }
             }
         const double gr = -P->grav / P->rho_0;
+#pragma omp parallel for schedule(static)
         for (int i = 2; i < N - 2; i++)
             for (int j = 2; j < M - 2; j++)
                 for (int k = 0; k < nz - 1; k++) {

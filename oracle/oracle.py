@@ -44,6 +44,14 @@ def lib():
     return _LIB
 
 
+def num_threads():
+    return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(ctypes.c_int(int(n)))
+
+
 def _p(arr):
     return None if arr is None else arr.ctypes.data_as(ctypes.c_void_p)
 

@@ -48,7 +48,8 @@ static const T* unpack(const char* opaque, size_t len, const char* who) {
 static bool valid_iso(const VerosB200IsoDescriptor* d, const char* who) {
     if (!d) return false;
     if (d->nx_tot < 5 || d->ny_tot < 5 || d->nz < 2 || d->eq_of_state_type < 1 || d->eq_of_state_type > 5 ||
-        (size_t)d->nx_tot * d->ny_tot * d->nz > (size_t)1 << 31 || !(d->iso_dslope != 0.0) || !(d->dt_tracer != 0.0)) {
+        (size_t)d->nx_tot * d->ny_tot * d->nz > (size_t)1 << 31 || !(d->iso_dslope > 0.0) || !(d->dt_tracer != 0.0) ||
+        !(d->iso_slopec >= 0.0) || !(d->iso_slopec / d->iso_dslope <= 300.0)) {
         set_error(VEROS_B200_ERR_BAD_ARGUMENT, who);
         return false;
     }
@@ -141,6 +142,9 @@ void veros_b200_iso_pre_f64(void* stream, void** B, const char* opaque, size_t l
     a.K_33 = (double*)B[30];
     a.drdT = (double*)B[31];
     a.drdS = a.drdT + n3;
+    a.with_flux = 0;
+    for (int t = 0; t < 2; ++t)
+        for (int q = 0; q < 3; ++q) a.flux[t][q] = nullptr;
     a.eos = d->eq_of_state_type;
     a.K_iso_steep = d->K_iso_steep;
     a.iso_slopec = d->iso_slopec;
@@ -180,6 +184,7 @@ void veros_b200_iso_diffusion_f64(void* stream, void** B, const char* opaque, si
     a.kbot = (const int32_t*)B[15];
     a.skew = (d->flags & VEROS_B200_FLAG_SKEW) ? 1 : 0;
     a.energy = energy ? 1 : 0;
+    a.fluxes_ready = 0;
     a.dt_tracer = d->dt_tracer;
     a.grav = d->grav;
     a.rho_0 = d->rho_0;
@@ -214,8 +219,11 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     p.K_11 = (double*)B[40];
     p.K_22 = (double*)B[41];
     p.K_33 = (double*)B[42];
-    p.drdT = ws;  // shares the front of the workspace with the fluxes (consumed before they are written)
-    p.drdS = ws + n3;
+    p.drdT = ws + 6 * n3;  // behind the six flux arrays
+    p.drdS = ws + 7 * n3;
+    p.with_flux = 1;
+    for (int t = 0; t < 2; ++t)
+        for (int q = 0; q < 3; ++q) p.flux[t][q] = ws + (size_t)(3 * t + q) * n3;
     p.eos = d->eq_of_state_type;
     p.K_iso_steep = d->K_iso_steep;
     p.iso_slopec = d->iso_slopec;
@@ -248,6 +256,7 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     a.kbot = (const int32_t*)B[19];
     a.skew = 0;
     a.energy = energy ? 1 : 0;
+    a.fluxes_ready = 1;
     a.dt_tracer = d->dt_tracer;
     a.grav = d->grav;
     a.rho_0 = d->rho_0;
@@ -267,8 +276,7 @@ size_t veros_b200_iso_diffusion_workspace_bytes(const char* opaque, size_t len) 
 size_t veros_b200_iso_step_workspace_bytes(const char* opaque, size_t len) {
     const auto* d = unpack<VerosB200IsoDescriptor>(opaque, len, "iso_step_workspace_bytes: bad descriptor");
     if (!d) return 0;
-    const size_t a = pre_ws_doubles(d), b = diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 2);
-    return 8 * (a > b ? a : b);
+    return 8 * (pre_ws_doubles(d) + diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 2));
 }
 
 int veros_b200_last_error(void) { return g_err.load(); }

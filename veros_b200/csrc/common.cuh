@@ -29,6 +29,8 @@ struct PreArgs {
     const uint8_t *maskT, *maskU, *maskV, *maskW;
     double *Ai_ez, *Ai_nz, *Ai_bx, *Ai_by, *K_11, *K_22, *K_33;
     double *drdT, *drdS;  // workspace, EOS 5 only
+    double* flux[2][3];   // [temp|salt][east|north|top] outputs when with_flux
+    int with_flux;
     int eos;
     double K_iso_steep, iso_slopec, iso_dslope;
 };
@@ -50,6 +52,7 @@ struct DiffArgs {
     const uint8_t *maskT, *maskW;
     const int32_t* kbot;
     int skew, energy;
+    int fluxes_ready;  // the fused slope+flux kernel already filled the flux workspace
     double dt_tracer, grav, rho_0;
 };
 

@@ -151,15 +151,23 @@ flux_kernel(const DiffArgs a, const int t, double* __restrict__ flux_east, doubl
 
 // ------------------------------------------------------------------------------------------------
 // update_kernel: grid (tiles over j in [1, M-1), planes i in [1, N-1)).  A tile is `cols` whole
-// columns of one x-plane = one contiguous piece of every (N,M,nz) array.
-// Shared memory (doubles, column pitch odd): L, D, U, R[NTR], DISS[NTR] (ENERGY), metric tables.
+// columns of one x-plane = one contiguous piece of every (N,M,nz) array.  Small CTAs (128 threads,
+// ~600 cells) so that several are resident per SM and the latency-bound column solves of one
+// overlap the streaming phases of the others.
+// Shared memory (doubles, odd column pitch): L, D, U, R[NTR] + metric tables.
+//   phase B  per cell: explicit flux divergence, tracer + tendency update, right-hand sides, matrix
+//   phase C  per column: dgtsv elimination on NTR right-hand sides (tdma_device.cuh)
+//   phase D  per cell: implicit result, tendency, dissipation (the T-point dissipation of levels
+//            k and k+1 is recomputed from the fluxes instead of being staged)
 // ------------------------------------------------------------------------------------------------
 struct Scratch {
     const double *fe[2], *fn[2], *ft[2];
 };
 
+constexpr int kUpdBlock = 128;
+
 template <int NTR, bool SKEW, bool ENERGY>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kUpdBlock, 6)
 update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch, const double fac_diss,
               const double gr) {
     extern __shared__ double sm[];
@@ -173,22 +181,21 @@ update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch
     double* D = L + tile;
     double* U = D + tile;
     double* R[2] = {U + tile, U + tile * 2};
-    double* DISS[2] = {U + tile * (1 + NTR), U + tile * (2 + NTR)};
-    double* tab = U + tile * (1 + NTR + (ENERGY ? NTR : 0));
-    Divisor* ddzt = reinterpret_cast<Divisor*>(tab);  // dzt[k]
-    Divisor* ddzw = ddzt + nz;                        // dzw[k]
-    double* dt_dzw = reinterpret_cast<double*>(ddzw + nz);  // dt_tracer / dzw[k]
-    Divisor* dcdxt = reinterpret_cast<Divisor*>(dt_dzw + nz);  // cost[j]*dxt[i]
-    Divisor* dcdyt = dcdxt + cols;                              // cost[j]*dyt[j]
-    int* ksv = reinterpret_cast<int*>(dcdyt + cols);            // kbot-1 per column
+    double* tab = U + tile * (1 + NTR);
+    Divisor* ddzt = reinterpret_cast<Divisor*>(tab);             // dzt[k]
+    Divisor* ddzw = ddzt + nz;                                   // dzw[k]
+    double* dt_dzw = reinterpret_cast<double*>(ddzw + nz);       // dt_tracer / dzw[k]
+    Divisor* dcdxt = reinterpret_cast<Divisor*>(dt_dzw + nz);    // cost[j]*dxt[i]
+    Divisor* dcdyt = dcdxt + cols;                               // cost[j]*dyt[j]
+    int* ksv = reinterpret_cast<int*>(dcdyt + cols);             // kbot-1 per column
 
     const double dt = a.dt_tracer;
-    for (int k = threadIdx.x; k < nz; k += blockDim.x) {
+    for (int k = threadIdx.x; k < nz; k += kUpdBlock) {
         ddzt[k] = make_divisor(a.g.dzt[k]);
         ddzw[k] = make_divisor(a.g.dzw[k]);
         dt_dzw[k] = strict::div(dt, a.g.dzw[k]);
     }
-    for (int q = threadIdx.x; q < ncols; q += blockDim.x) {
+    for (int q = threadIdx.x; q < ncols; q += kUpdBlock) {
         const int j = j0 + q;
         dcdxt[q] = make_divisor(mul(a.g.cost[j], a.g.dxt[i]));
         dcdyt[q] = make_divisor(mul(a.g.cost[j], a.g.dyt[j]));
@@ -203,71 +210,67 @@ update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch
     const int ncells = ncols * nz;
     const bool i_int = (i >= 2 && i < N - 2);
 
-    // ---- phase B: explicit part, rhs, matrix, dissipation on T points ---------------------------
-    for (int idx = threadIdx.x; idx < ncells; idx += blockDim.x) {
-        const int q = idx / nz, k = idx - q * nz;
-        const int j = j0 + q;
-        const size_t c = base + idx;
-        const int s = q * pitch + k;
-        const bool interior = i_int && j >= 2 && j < M - 2;
+    // ---- phase B --------------------------------------------------------------------------------
+    if (i_int) {
+        for (int idx = threadIdx.x; idx < ncells; idx += kUpdBlock) {
+            const int q = idx / nz, k = idx - q * nz;
+            const int j = j0 + q;
+            if (j < 2 || j >= M - 2) continue;
+            const size_t c = base + idx;
+            const int s = q * pitch + k;
+            const double mT = (double)a.maskT[c];
 #pragma unroll
-        for (int t = 0; t < NTR; ++t) {
-            const double fe_c = __ldg(f.fe[t] + c), fe_w = __ldg(f.fe[t] + c - plane);
-            const double fn_c = __ldg(f.fn[t] + c), fn_s = __ldg(f.fn[t] + c - nz);
-            if (interior) {
-                const double mT = (double)a.maskT[c];
+            for (int t = 0; t < NTR; ++t) {
+                const double fe_c = __ldg(f.fe[t] + c), fe_w = __ldg(f.fe[t] + c - plane);
+                const double fn_c = __ldg(f.fn[t] + c), fn_s = __ldg(f.fn[t] + c - nz);
                 const double ft_c = __ldg(f.ft[t] + c);
+                const double ft_m = k > 0 ? __ldg(f.ft[t] + c - 1) : 0.0;
                 double e = mul(mT, add(strict::div(sub(fe_c, fe_w), dcdxt[q]), strict::div(sub(fn_c, fn_s), dcdyt[q])));
                 if (k == 0)
                     e = add(e, strict::div(mul(mT, ft_c), ddzt[0]));
                 else
-                    e = add(e, strict::div(mul(mT, sub(ft_c, __ldg(f.ft[t] + c - 1))), ddzt[k]));
-                a.t[t].dtracer[c] = add(a.t[t].dtracer[c], e);            // diffusion.py:196
+                    e = add(e, strict::div(mul(mT, sub(ft_c, ft_m)), ddzt[k]));
+                a.t[t].dtracer[c] = add(a.t[t].dtracer[c], e);              // diffusion.py:196
                 const double v = add(a.t[t].tr[c * 3 + taup1], mul(dt, e));  // diffusion.py:197
                 a.t[t].tr[c * 3 + taup1] = v;
                 if (!SKEW) R[t][s] = v;
             }
-            if (ENERGY) {  // compute_dissipation, veros/core/diffusion.py:15-35 (on [1:-1, 1:-1])
-                const double* __restrict__ X = a.t[t].int_drhodX + tau;
-                const double xc = ldt(X, c);
-                const double gx = add(mul(sub(ldt(X, c + plane), xc), fe_c), mul(sub(xc, ldt(X, c - plane)), fe_w));
-                const double gy = add(mul(sub(ldt(X, c + nz), xc), fn_c), mul(sub(xc, ldt(X, c - nz)), fn_s));
-                DISS[t][s] = add(strict::div(mul(fac_diss, gx), dcdxt[q]), strict::div(mul(fac_diss, gy), dcdyt[q]));
+            if (!SKEW) {  // _calc_implicit_part, diffusion.py:149-164
+                const int ks = ksv[q];
+                const double del = (k < nz - 1) ? mul(dt_dzw[k], __ldg(a.K_33 + c)) : 0.0;
+                const double delm = (k > 0) ? mul(dt_dzw[k - 1], __ldg(a.K_33 + c - 1)) : 0.0;
+                double b;
+                if (k == ks)
+                    b = add(1.0, strict::div(del, ddzt[k]));  // b_tri_edge
+                else if (k == nz - 1)
+                    b = add(1.0, strict::div(delm, ddzt[k]));
+                else
+                    b = add(1.0, strict::div(add(del, delm), ddzt[k]));
+                D[s] = b;
+                U[s] = (k < nz - 1) ? strict::div(-del, ddzt[k]) : 0.0;
+                if (k > 0) L[s - 1] = (k > ks) ? strict::div(-delm, ddzt[k]) : 0.0;
             }
         }
-        if (!SKEW && interior) {  // _calc_implicit_part, diffusion.py:149-164
-            const int ks = ksv[q];
-            const double del = (k < nz - 1) ? mul(dt_dzw[k], __ldg(a.K_33 + c)) : 0.0;
-            const double delm = (k > 0) ? mul(dt_dzw[k - 1], __ldg(a.K_33 + c - 1)) : 0.0;
-            double b;
-            if (k == ks)
-                b = add(1.0, strict::div(del, ddzt[k]));  // b_tri_edge
-            else if (k == nz - 1)
-                b = add(1.0, strict::div(delm, ddzt[k]));
-            else
-                b = add(1.0, strict::div(add(del, delm), ddzt[k]));
-            D[s] = b;
-            U[s] = (k < nz - 1) ? strict::div(-del, ddzt[k]) : 0.0;
-            if (k > 0) L[s - 1] = (k > ks) ? strict::div(-delm, ddzt[k]) : 0.0;
-        }
     }
-    __syncthreads();
 
-    // ---- phase C: one thread per water column, dgtsv on both right-hand sides -------------------
-    if (!SKEW && i_int) {
-        for (int q = threadIdx.x; q < ncols; q += blockDim.x) {
-            const int j = j0 + q;
-            const int ks = ksv[q];
-            if (j >= 2 && j < M - 2 && ks >= 0) {
-                const int o = q * pitch;
-                dgtsv_column<NTR>(ks, nz, 1, L + o, D + o, U + o, R[0] + o, R[NTR - 1] + o);
+    // ---- phase C: one thread per water column, dgtsv on all right-hand sides ----------------------
+    if (!SKEW) {
+        __syncthreads();
+        if (i_int) {
+            for (int q = threadIdx.x; q < ncols; q += kUpdBlock) {
+                const int j = j0 + q;
+                const int ks = ksv[q];
+                if (j >= 2 && j < M - 2 && ks >= 0) {
+                    const int o = q * pitch;
+                    dgtsv_column<NTR>(ks, nz, 1, L + o, D + o, U + o, R[0] + o, R[NTR - 1] + o);
+                }
             }
         }
         __syncthreads();
     }
 
-    // ---- phase D: tracer, tendency, dissipation -------------------------------------------------
-    for (int idx = threadIdx.x; idx < ncells; idx += blockDim.x) {
+    // ---- phase D ----------------------------------------------------------------------------------
+    for (int idx = threadIdx.x; idx < ncells; idx += kUpdBlock) {
         const int q = idx / nz, k = idx - q * nz;
         const int j = j0 + q;
         const size_t c = base + idx;
@@ -286,20 +289,36 @@ update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch
                 a.t[t].tr[c * 3 + taup1] = nw;
             }
             if (ENERGY) {
+                // compute_dissipation (veros/core/diffusion.py:15-35) at levels k and k+1 of this column
+                const double* __restrict__ X = a.t[t].int_drhodX + tau;
+                const bool up = k < nz - 1;
+                double dk[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (u == 1 && !up) {
+                        dk[1] = 0.0;
+                        break;
+                    }
+                    const size_t cc = c + u;
+                    const double xc = ldt(X, cc);
+                    const double fe_c = __ldg(f.fe[t] + cc), fe_w = __ldg(f.fe[t] + cc - plane);
+                    const double fn_c = __ldg(f.fn[t] + cc), fn_s = __ldg(f.fn[t] + cc - nz);
+                    const double gx = add(mul(sub(ldt(X, cc + plane), xc), fe_c), mul(sub(xc, ldt(X, cc - plane)), fe_w));
+                    const double gy = add(mul(sub(ldt(X, cc + nz), xc), fn_c), mul(sub(xc, ldt(X, cc - nz)), fn_s));
+                    dk[u] = add(strict::div(mul(fac_diss, gx), dcdxt[q]), strict::div(mul(fac_diss, gy), dcdyt[q]));
+                }
                 // dissipation_on_wgrid, veros/core/diffusion.py:41-62
-                const double dk = DISS[t][s];
                 double dw;
-                if (k < nz - 1) {
-                    const double m = mul(0.5, add(dk, DISS[t][s + 1]));
+                if (up) {
+                    const double m = mul(0.5, add(dk[0], dk[1]));
                     const double edge = (land && k == ks) ? 1.0 : 0.0, water = (land && k > ks) ? 1.0 : 0.0;
                     const double dzw_pad = a.g.dzw[k > 0 ? k - 1 : 0];
-                    dw = add(mul(add(m, mul(0.5, strict::div(mul(dk, dzw_pad), ddzw[k]))), edge), mul(m, water));
+                    dw = add(mul(add(m, mul(0.5, strict::div(mul(dk[0], dzw_pad), ddzw[k]))), edge), mul(m, water));
                 } else {
-                    dw = mul(dk, land ? 1.0 : 0.0);
+                    dw = mul(dk[0], land ? 1.0 : 0.0);
                 }
                 P = add(P, dw);  // diffusion.py:246-249
-                if (interior && k < nz - 1) {  // diffusion.py:254-279
-                    const double* __restrict__ X = a.t[t].int_drhodX + tau;
+                if (interior && up) {  // diffusion.py:254-279
                     const double fxa = strict::div(add(-ldt(X, c + 1), ldt(X, c)), ddzw[k]);
                     const double mW = (double)a.maskW[c];
                     const double ft_c = __ldg(f.ft[t] + c);
@@ -324,17 +343,18 @@ template <int NTR, bool SKEW, bool ENERGY>
 void launch_update(cudaStream_t s, const DiffArgs& a, const Scratch& f) {
     const int M = a.g.M, N = a.g.N, nz = a.g.nz;
     const int pitch = nz | 1;
-    const int narr = 3 + NTR + (ENERGY ? NTR : 0);
-    int cols = (56 * 1024) / (narr * 8 * pitch);
-    cols = max(1, min(cols, M - 2));
-    const int want_tiles = 2 * 148;  // small grids: spread over the SMs
+    const int narr = SKEW ? 0 : 3 + NTR;
+    int cols = max(1, 640 / nz);
+    cols = min(cols, M - 2);
+    const int want_tiles = 4 * 148;  // small grids: spread over the SMs
     const int rows = N - 2;
     if (((M - 2 + cols - 1) / cols) * rows < want_tiles) {
         const int per_row = (want_tiles + rows - 1) / rows;
         cols = max(1, (M - 2 + per_row - 1) / per_row);
     }
-    const size_t smem = (size_t)narr * 8 * cols * pitch + (size_t)nz * (2 * sizeof(Divisor) + 8) +
+    const size_t smem = (size_t)(3 + NTR) * 8 * cols * pitch + (size_t)nz * (2 * sizeof(Divisor) + 8) +
                         (size_t)cols * (2 * sizeof(Divisor) + sizeof(int)) + 16;
+    (void)narr;
     auto kern = update_kernel<NTR, SKEW, ENERGY>;
     static bool configured = false;
     if (!configured) {
@@ -344,7 +364,7 @@ void launch_update(cudaStream_t s, const DiffArgs& a, const Scratch& f) {
     dim3 grid((M - 2 + cols - 1) / cols, N - 2);
     const double fac_diss = 0.5 * a.grav / a.rho_0;  // diffusion.py (core) :19-21, Python float arithmetic
     const double gr = -a.grav / a.rho_0;             // isoneutral/diffusion.py:259,268
-    kern<<<grid, 256, smem, s>>>(a, f, cols, pitch, fac_diss, gr);
+    kern<<<grid, kUpdBlock, smem, s>>>(a, f, cols, pitch, fac_diss, gr);
     count_launch();
     check_launch("update_kernel");
 }
@@ -366,6 +386,7 @@ void launch_iso_diffusion_ws(cudaStream_t s, const DiffArgs& a, double* ws) {
         f.fe[t] = fe;
         f.fn[t] = fn;
         f.ft[t] = ft;
+        if (a.fluxes_ready) continue;
         const int block = 256;
         dim3 grid((M * nz + block - 1) / block, N);
         const int jr = block / nz + 2;

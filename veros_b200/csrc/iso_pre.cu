@@ -1,47 +1,111 @@
-// isoneutral_diffusion_pre (veros/core/isoneutral/isoneutral.py:18-229): density-triad slopes,
-// Ai_ez / Ai_nz / Ai_bx / Ai_by and the mixing tensor K_11 / K_22 / K_33, one pass over the grid.
+// isoneutral_diffusion_pre (veros/core/isoneutral/isoneutral.py:18-229) fused with the tracer
+// fluxes of isoneutral_diffusion (veros/core/isoneutral/diffusion.py:9-113) for temp and salt.
 //
 // One thread owns one T cell (i,j,k) and produces everything the reference stores at that index:
-// the east-face, north-face and top-face triads (16 slopes).  Threads are laid out along the
-// flattened (j,k) index of an x-plane, i.e. along memory, so every load and store of a warp is
-// contiguous; the 2x2 blocks of the Ai_* arrays are written as two 16-byte stores per thread.
-// Nothing intermediate (gradients, drdT/drdS, diffloc, sums) ever goes to HBM, except drdT/drdS
-// for the 48-term TEOS-10 equation of state, which a small pre-pass evaluates once per cell.
+// the east-, north- and top-face triads (16 slopes -> Ai_ez, Ai_nz, Ai_bx, Ai_by, K_11, K_22, K_33)
+// and, when FLUX is set, flux_east / flux_north / flux_top of both tracers, computed from the Ai
+// values while they are still in registers (the stand-alone op re-reads 128 B/cell for each tracer).
+// Threads run along the flattened (j,k) index of an x-plane, i.e. along memory: every load and
+// store of a warp is contiguous; the 2x2 blocks of Ai_* leave as 16-byte stores.
 //
-// Arithmetic: this kernel is FP64-pipe bound, not HBM bound (16 divisions + 16 tanh per cell in
-// the reference formulation).  Divisions by grid metrics are multiplications by reciprocals and
-// 0.5*(1+tanh(x)) is evaluated through one exp and one reciprocal; results agree with the
-// reference to ~1e-15 (tests/test_gpu_parity.py), they are not bit-identical (neither are NumPy's
-// SIMD tanh and libm's).
+// This kernel is bound by the FP64 pipe and by instruction issue, not by HBM (ncu: profiles/), so
+// the design goal is instructions per cell:
+//   * every division by a grid metric is a multiplication by a reciprocal tabulated once per CTA
+//     in shared memory (the same tables hold the correctly rounded reciprocals the strict flux
+//     arithmetic needs, strict.cuh);
+//   * 0.5*(1+tanh(x)) = 1/(1+exp(-2x)) costs one branch-free exp (64-entry 2^(j/64) table in
+//     shared memory + degree-5 polynomial) and one Newton reciprocal seeded by rcp.approx;
+//   * slope denominators use the same branch-free reciprocal; the four x- and four y-slopes of a
+//     top face share two of them;
+//   * masks enter as selects folded into the metric factors, never as int->double conversions.
+// Slopes/diffusivities agree with the reference to ~1e-15 of their maximum (tests/), not bit for
+// bit (NumPy's SIMD tanh is not reproducible either).  The FLUXES are strict: given the stored Ai_*
+// and K_* they are bit-identical to the reference's expressions (flux_device.cuh).
 #include "common.cuh"
 #include "eos.cuh"
+#include "flux_device.cuh"
 
 namespace vb {
 
 namespace {
 
+using strict::Divisor;
+using strict::make_divisor;
+
 constexpr double kEps = 1e-20;  // isoneutral.py:28
 
-struct TaperParams {
-    double c0;       // iso_slopec / iso_dslope
-    double rdslope;  // 1 / iso_dslope
+__constant__ double c_exp2_table[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+
+// 1/x for normal finite x with 1/x normal: rcp.approx (>= 20 good bits) + one cubic Newton step.
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
+}
+
+// exp(u) for u in [-700, 700], relative error < 4e-16, no branches.
+//   u = (64 n + j) ln2/64 + r,  exp(u) = 2^n * 2^(j/64) * (1 + r q(r)),  |r| <= ln2/128
+__device__ __forceinline__ double exp_fast(double u, const double* __restrict__ tab) {
+    constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer in the low word
+    double t = fma(u, 0x1.71547652b82fep+6, kMagic);
+    const int ni = __double2loint(t);
+    t -= kMagic;
+    double r = fma(t, -0x1.62e42fe000000p-7, u);
+    r = fma(t, -0x1.f473de6af278fp-36, r);
+    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    const double p = r * q;
+    const double T = tab[ni & 63];
+    const double e = fma(T, p, T);
+    return __hiloint2double(__double2hiint(e) + ((ni >> 6) << 20), __double2loint(e));
+}
+
+struct Taper {
+    double two_rd;   // 2 / iso_dslope
+    double m2c0;     // -2 iso_slopec / iso_dslope
+    double s_max;    // |s| beyond which exp(-2x) would overflow; the taper is exactly 0 there anyway
+    const double* tab;
+    // dm_taper (isoneutral.py:10-15): 0.5*(1+tanh(x)), x = (slopec-|s|)/dslope, as 1/(1+exp(-2x)).
+    // "2q - 1" is rounded like a tanh value, so 1 + tanh(x) quantises to multiples of 2^-53 near -1
+    // exactly as the reference's does (the taper is exactly 0 for x < -18.4).
+    __device__ __forceinline__ double operator()(double s) const {
+        const double sa = fmin(fabs(s), s_max);
+        const double u = fma(sa, two_rd, m2c0);
+        const double e = exp_fast(u, tab);
+        const double q = rcp_fast(1.0 + e);
+        const double th = fma(2.0, q, -1.0);
+        return fma(0.5, th, 0.5);
+    }
 };
 
-// dm_taper (isoneutral.py:10-15): 0.5*(1+tanh(x)), x = (-|s| + slopec)/dslope.
-// tanh(x) = 2/(1+exp(-2x)) - 1.  The intermediate "2q - 1" is rounded like the reference's tanh
-// value so that 1 + tanh(x) quantises to multiples of 2^-53 near -1 exactly as NumPy's does
-// (the taper is exactly 0 for x < -18.4).
-__device__ __forceinline__ double dm_taper(double s, const TaperParams& tp) {
-    const double x = fma(-fabs(s), tp.rdslope, tp.c0);
-    const double e = exp(-2.0 * x);
-    const double q = 1.0 / (1.0 + e);
-    const double th = fma(2.0, q, -1.0);
-    return 0.5 * (1.0 + th);
-}
+// min(0, x) - eps with two FP64 instructions: x - |x| is 2x or 0 exactly.
+__device__ __forceinline__ double neg_part_minus_eps(double x) { return fma(x - fabs(x), 0.5, -kEps); }
 
 __device__ __forceinline__ void store_pair(double* base, double v0, double v1) {
     *reinterpret_cast<double2*>(base) = make_double2(v0, v1);
 }
+
+__device__ __forceinline__ double sel(bool m, double v) { return m ? v : 0.0; }
 
 }  // namespace
 
@@ -60,12 +124,65 @@ eos5_kernel(size_t ncell, int nz, const double* __restrict__ temp, const double*
     drdS[c] = dS;
 }
 
-template <int EOS>
-__global__ void __launch_bounds__(128)
+// Shared-memory tables of one CTA (plane i, flattened cells [p0, p0 + blockDim)):
+//   per level k:  d4zt = 4 dzt[k] (+ reciprocal), rdzw = 1/dzw[k], dzw[k], |zt[k]|
+//   per row j in [jlo-1, jhi]:  cost*dxu[i], 1/(cost*dxu[i-1]), dyu, cost, (4 dyt) cost (+ reciprocals),
+//                               cosu, cosu*dyu
+struct RowTab {
+    Divisor cdxu, dyu, cost, d4ytc;
+    double r_cdxu_w, cosu, facty, pad;
+};
+struct LevTab {
+    Divisor d4zt;
+    double rdzw, dzw, pabs, pad;
+};
+
+constexpr int kPreBlock = 128;
+
+template <int EOS, bool FLUX>
+__global__ void __launch_bounds__(kPreBlock)
 iso_pre_kernel(const PreArgs a) {
+    extern __shared__ double sm[];
     const int N = a.g.N, M = a.g.M, nz = a.g.nz;
     const int i = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p0 = blockIdx.x * kPreBlock;
+    const int jlo = max(p0 / nz - 1, 0);
+    const int jhi = min(M - 1, (p0 + kPreBlock - 1) / nz);
+    const int jr = jhi - jlo + 1;
+
+    double* tab = sm;                                        // 64 doubles
+    LevTab* lev = reinterpret_cast<LevTab*>(tab + 64);       // nz
+    RowTab* row = reinterpret_cast<RowTab*>(lev + nz);       // jr
+    Divisor* d4xt = reinterpret_cast<Divisor*>(row + jr);    // 1
+    const int iw = max(i - 1, 0);
+    if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_table[threadIdx.x];
+    if (threadIdx.x == 64) d4xt[0] = make_divisor(4.0 * a.g.dxt[i]);
+    for (int k = threadIdx.x; k < nz; k += kPreBlock) {
+        LevTab t;
+        t.d4zt = make_divisor(4.0 * a.g.dzt[k]);
+        t.dzw = a.g.dzw[k];
+        t.rdzw = 1.0 / t.dzw;
+        t.pabs = fabs(a.g.zt[k]);
+        t.pad = 0.0;
+        lev[k] = t;
+    }
+    for (int q = threadIdx.x; q < jr; q += kPreBlock) {
+        const int j = jlo + q;
+        RowTab t;
+        const double cost = a.g.cost[j], dyu = a.g.dyu[j], cosu = a.g.cosu[j];
+        t.cdxu = make_divisor(cost * a.g.dxu[i]);
+        t.r_cdxu_w = 1.0 / (a.g.dxu[iw] * cost);
+        t.dyu = make_divisor(dyu);
+        t.cost = make_divisor(cost);
+        t.d4ytc = make_divisor(4.0 * a.g.dyt[j] * cost);
+        t.cosu = cosu;
+        t.facty = cosu * dyu;
+        t.pad = 0.0;
+        row[q] = t;
+    }
+    __syncthreads();
+
+    const int p = p0 + threadIdx.x;
     if (p >= M * nz) return;
     const int j = p / nz;
     const int k = p - j * nz;
@@ -77,239 +194,262 @@ iso_pre_kernel(const PreArgs a) {
     const bool inE = (i >= 1 && i < N - 2 && j >= 2 && j < M - 2);
     const bool inN = (i >= 2 && i < N - 2 && j >= 1 && j < M - 2);
     const bool inT = (i >= 2 && i < N - 2 && j >= 2 && j < M - 2 && k < nz - 1);
-    if (!(inE || inN || inT)) return;
+    double fl[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};  // [tracer][east, north, top]
 
-    const int tau = *a.tau;
-    const double* __restrict__ T = a.temp + tau;
-    const double* __restrict__ S = a.salt + tau;
-    auto ld = [](const double* f, size_t cell) { return __ldg(f + cell * 3); };
+    if (inE || inN || inT) {
+        const int tau = *a.tau;
+        const double* __restrict__ T = a.temp + tau;
+        const double* __restrict__ S = a.salt + tau;
+        auto ld = [](const double* f, size_t cell) { return __ldg(f + cell * 3); };
+        const bool hasKm = k >= 1, hasKp = k < nz - 1;
+        const int km = hasKm ? -1 : 0, kp = hasKp ? 1 : 0;  // clamped neighbours (pad_z_edges)
+        const size_t ce = c + plane, cn = c + nz, cw = c - plane, cs = c - nz;
+        const LevTab L1 = lev[k];
+        const LevTab L0 = lev[k + km];
+        const RowTab Rj = row[j - jlo];
+        const Taper taper = {2.0 / a.iso_dslope, -2.0 * a.iso_slopec / a.iso_dslope,
+                             (345.0 + a.iso_slopec / a.iso_dslope) * a.iso_dslope, tab};
 
-    const bool hasKm = k >= 1, hasKp = k < nz - 1;
-    const size_t ce = c + plane, cn = c + nz, cw = c - plane, cs = c - nz;
+        // ---- this column: values, vertical differences and gradients ------------------------------
+        const double Tc = ld(T, c), Sc = ld(S, c);
+        const double Tm = ld(T, c + km), Sm = ld(S, c + km);
+        const double Tp = ld(T, c + kp), Sp = ld(S, c + kp);
+        const double dT0c = Tc - Tm, dS0c = Sc - Sm;  // level k-1 (0 at the bottom)
+        const double dT1c = Tp - Tc, dS1c = Sp - Sc;  // level k   (0 at the surface)
+        const bool mWc1 = hasKp && a.maskW[c], mWc0 = hasKm && a.maskW[c + km];
+        const double w1c = sel(mWc1, L1.rdzw), w0c = sel(mWc0, L0.rdzw);
+        const double gTz1c = dT1c * w1c, gSz1c = dS1c * w1c;  // dTdz(i,j,k)
+        const double gTz0c = dT0c * w0c, gSz0c = dS0c * w0c;  // dTdz(i,j,k-1)
 
-    // ---- tracer values ------------------------------------------------------------------------
-    const double Tc = ld(T, c), Sc = ld(S, c);
-    const double Tkm = hasKm ? ld(T, c - 1) : 0.0, Skm = hasKm ? ld(S, c - 1) : 0.0;
-    const double Tkp = hasKp ? ld(T, c + 1) : 0.0, Skp = hasKp ? ld(S, c + 1) : 0.0;
-
-    const double rdz1 = hasKp ? 1.0 / __ldg(a.g.dzw + k) : 0.0;      // level k   (between k and k+1)
-    const double rdz0 = hasKm ? 1.0 / __ldg(a.g.dzw + k - 1) : 0.0;  // level k-1
-    const double dzw1 = __ldg(a.g.dzw + k);
-    const double dzw0 = hasKm ? __ldg(a.g.dzw + k - 1) : 0.0;
-    const double pk = fabs(__ldg(a.g.zt + k));
-
-    // vertical gradients at this column: dTdz(i,j,k-1), dTdz(i,j,k)
-    const double mWc1 = hasKp ? (double)a.maskW[c] : 0.0;
-    const double mWc0 = hasKm ? (double)a.maskW[c - 1] : 0.0;
-    const double dTz_c1 = mWc1 * (Tkp - Tc) * rdz1, dSz_c1 = mWc1 * (Skp - Sc) * rdz1;
-    const double dTz_c0 = mWc0 * (Tc - Tkm) * rdz0, dSz_c0 = mWc0 * (Sc - Skm) * rdz0;
-
-    // drdT / drdS at this cell
-    double drT_c, drS_c;
-    if (Eos<EOS>::kExpensive) {
-        drT_c = __ldg(a.drdT + c);
-        drS_c = __ldg(a.drdS + c);
-    } else {
-        eos_drho<EOS>(Sc, Tc, pk, drT_c, drS_c);
-        const double m = (double)a.maskT[c];
-        drT_c *= m;
-        drS_c *= m;
-    }
-
-    const TaperParams tp = {a.iso_slopec / a.iso_dslope, 1.0 / a.iso_dslope};
-    const double rdzt4 = 1.0 / (4.0 * __ldg(a.g.dzt + k));
-
-    // ---- east face: Ai_ez, K_11 (isoneutral.py:100-132) ---------------------------------------
-    double Tke = 0.0, Ske = 0.0, Tkpe = 0.0, Skpe = 0.0;  // (i+1,j,k), (i+1,j,k+1): reused by the top face
-    if (inE || inT) {
-        Tke = ld(T, ce);
-        Ske = ld(S, ce);
-        if (hasKp) {
-            Tkpe = ld(T, ce + 1);
-            Skpe = ld(S, ce + 1);
-        }
-    }
-    const double rdx_c = 1.0 / (__ldg(a.g.dxu + i) * __ldg(a.g.cost + j));
-    const double mU_c = (double)a.maskU[c];
-    const double dTx_c = mU_c * (Tke - Tc) * rdx_c, dSx_c = mU_c * (Ske - Sc) * rdx_c;
-    if (inE) {
-        const double Tkme = hasKm ? ld(T, ce - 1) : 0.0, Skme = hasKm ? ld(S, ce - 1) : 0.0;
-        const double mWe1 = hasKp ? (double)a.maskW[ce] : 0.0;
-        const double mWe0 = hasKm ? (double)a.maskW[ce - 1] : 0.0;
-        const double dTz_e1 = mWe1 * (Tkpe - Tke) * rdz1, dSz_e1 = mWe1 * (Skpe - Ske) * rdz1;
-        const double dTz_e0 = mWe0 * (Tke - Tkme) * rdz0, dSz_e0 = mWe0 * (Ske - Skme) * rdz0;
-        double drT_e, drS_e;
+        double drTc, drSc;
         if (Eos<EOS>::kExpensive) {
-            drT_e = __ldg(a.drdT + ce);
-            drS_e = __ldg(a.drdS + ce);
+            drTc = __ldg(a.drdT + c);
+            drSc = __ldg(a.drdS + c);
         } else {
-            eos_drho<EOS>(Ske, Tke, pk, drT_e, drS_e);
-            const double m = (double)a.maskT[ce];
-            drT_e *= m;
-            drS_e *= m;
-        }
-        double diffloc;
-        if (hasKm)
-            diffloc = 0.25 * (__ldg(a.K_iso + c) + __ldg(a.K_iso + c - 1) + __ldg(a.K_iso + ce) + __ldg(a.K_iso + ce - 1));
-        else
-            diffloc = 0.5 * (__ldg(a.K_iso + c) + __ldg(a.K_iso + ce));
-
-        double A[2][2];  // [ip][kr]
-        double sumz = 0.0;
-#pragma unroll
-        for (int kr = 0; kr < 2; ++kr) {
-#pragma unroll
-            for (int ip = 0; ip < 2; ++ip) {
-                const double dT_ = ip ? drT_e : drT_c, dS_ = ip ? drS_e : drS_c;
-                const double tz = ip ? (kr ? dTz_e1 : dTz_e0) : (kr ? dTz_c1 : dTz_c0);
-                const double sz = ip ? (kr ? dSz_e1 : dSz_e0) : (kr ? dSz_c1 : dSz_c0);
-                const double drodxe = dT_ * dTx_c + dS_ * dSx_c;
-                const double drodze = dT_ * tz + dS_ * sz;
-                const double sxe = -drodxe / (fmin(0.0, drodze) - kEps);
-                const double taper = dm_taper(sxe, tp);
-                const double dz = kr ? dzw1 : dzw0;
-                if (kr == 1 || hasKm) sumz += dz * mU_c * fmax(a.K_iso_steep, diffloc * taper);
-                A[ip][kr] = taper * sxe * mU_c;
-            }
-        }
-        double* out = a.Ai_ez + c * 4;
-        if (hasKm) {
-            store_pair(out, A[0][0], A[0][1]);
-            store_pair(out + 2, A[1][0], A[1][1]);
-        } else {  // k = 0: the kr = 0 entries are never written (isoneutral.py:113-131, ki = 1)
-            out[1] = A[0][1];
-            out[3] = A[1][1];
-        }
-        a.K_11[c] = sumz * rdzt4;
-    }
-
-    // ---- north face: Ai_nz, K_22 (isoneutral.py:137-168) --------------------------------------
-    double Tkn = 0.0, Skn = 0.0, Tkpn = 0.0, Skpn = 0.0;  // (i,j+1,k), (i,j+1,k+1)
-    if (inN || inT) {
-        Tkn = ld(T, cn);
-        Skn = ld(S, cn);
-        if (hasKp) {
-            Tkpn = ld(T, cn + 1);
-            Skpn = ld(S, cn + 1);
-        }
-    }
-    const double rdy_c = 1.0 / __ldg(a.g.dyu + j);
-    const double mV_c = (double)a.maskV[c];
-    const double dTy_c = mV_c * (Tkn - Tc) * rdy_c, dSy_c = mV_c * (Skn - Sc) * rdy_c;
-    if (inN) {
-        const double Tkmn = hasKm ? ld(T, cn - 1) : 0.0, Skmn = hasKm ? ld(S, cn - 1) : 0.0;
-        const double mWn1 = hasKp ? (double)a.maskW[cn] : 0.0;
-        const double mWn0 = hasKm ? (double)a.maskW[cn - 1] : 0.0;
-        const double dTz_n1 = mWn1 * (Tkpn - Tkn) * rdz1, dSz_n1 = mWn1 * (Skpn - Skn) * rdz1;
-        const double dTz_n0 = mWn0 * (Tkn - Tkmn) * rdz0, dSz_n0 = mWn0 * (Skn - Skmn) * rdz0;
-        double drT_n, drS_n;
-        if (Eos<EOS>::kExpensive) {
-            drT_n = __ldg(a.drdT + cn);
-            drS_n = __ldg(a.drdS + cn);
-        } else {
-            eos_drho<EOS>(Skn, Tkn, pk, drT_n, drS_n);
-            const double m = (double)a.maskT[cn];
-            drT_n *= m;
-            drS_n *= m;
-        }
-        double diffloc;
-        if (hasKm)
-            diffloc = 0.25 * (__ldg(a.K_iso + c) + __ldg(a.K_iso + c - 1) + __ldg(a.K_iso + cn) + __ldg(a.K_iso + cn - 1));
-        else
-            diffloc = 0.5 * (__ldg(a.K_iso + c) + __ldg(a.K_iso + cn));
-
-        double A[2][2];  // [jp][kr]
-        double sumz = 0.0;
-#pragma unroll
-        for (int kr = 0; kr < 2; ++kr) {
-#pragma unroll
-            for (int jp = 0; jp < 2; ++jp) {
-                const double dT_ = jp ? drT_n : drT_c, dS_ = jp ? drS_n : drS_c;
-                const double tz = jp ? (kr ? dTz_n1 : dTz_n0) : (kr ? dTz_c1 : dTz_c0);
-                const double sz = jp ? (kr ? dSz_n1 : dSz_n0) : (kr ? dSz_c1 : dSz_c0);
-                const double drodyn = dT_ * dTy_c + dS_ * dSy_c;
-                const double drodzn = dT_ * tz + dS_ * sz;
-                const double syn = -drodyn / (fmin(0.0, drodzn) - kEps);
-                const double taper = dm_taper(syn, tp);
-                const double dz = kr ? dzw1 : dzw0;
-                if (kr == 1 || hasKm) sumz += dz * mV_c * fmax(a.K_iso_steep, diffloc * taper);
-                A[jp][kr] = taper * syn * mV_c;
-            }
-        }
-        double* out = a.Ai_nz + c * 4;
-        if (hasKm) {
-            store_pair(out, A[0][0], A[0][1]);
-            store_pair(out + 2, A[1][0], A[1][1]);
-        } else {
-            out[1] = A[0][1];
-            out[3] = A[1][1];
-        }
-        a.K_22[c] = sumz * rdzt4;
-    }
-
-    // ---- top face: Ai_bx, Ai_by, K_33 (isoneutral.py:173-225) ---------------------------------
-    if (inT) {
-        // x and y gradients on the faces around (i,j) at levels k and k+1
-        const double rdx_w = 1.0 / (__ldg(a.g.dxu + i - 1) * __ldg(a.g.cost + j));
-        const double rdy_s = 1.0 / __ldg(a.g.dyu + j - 1);
-        const double Tw = ld(T, cw), Sw = ld(S, cw), Tkpw = ld(T, cw + 1), Skpw = ld(S, cw + 1);
-        const double Ts = ld(T, cs), Ss = ld(S, cs), Tkps = ld(T, cs + 1), Skps = ld(S, cs + 1);
-        const double mU_cu = (double)a.maskU[c + 1], mU_w = (double)a.maskU[cw], mU_wu = (double)a.maskU[cw + 1];
-        const double mV_cu = (double)a.maskV[c + 1], mV_s = (double)a.maskV[cs], mV_su = (double)a.maskV[cs + 1];
-        // [ip or jp][kr]
-        const double dTx[2][2] = {{mU_w * (Tc - Tw) * rdx_w, mU_wu * (Tkp - Tkpw) * rdx_w},
-                                  {dTx_c, mU_cu * (Tkpe - Tkp) * rdx_c}};
-        const double dSx[2][2] = {{mU_w * (Sc - Sw) * rdx_w, mU_wu * (Skp - Skpw) * rdx_w},
-                                  {dSx_c, mU_cu * (Skpe - Skp) * rdx_c}};
-        const double dTy[2][2] = {{mV_s * (Tc - Ts) * rdy_s, mV_su * (Tkp - Tkps) * rdy_s},
-                                  {dTy_c, mV_cu * (Tkpn - Tkp) * rdy_c}};
-        const double dSy[2][2] = {{mV_s * (Sc - Ss) * rdy_s, mV_su * (Skp - Skps) * rdy_s},
-                                  {dSy_c, mV_cu * (Skpn - Skp) * rdy_c}};
-        double drT_u, drS_u;  // (i,j,k+1)
-        if (Eos<EOS>::kExpensive) {
-            drT_u = __ldg(a.drdT + c + 1);
-            drS_u = __ldg(a.drdS + c + 1);
-        } else {
-            eos_drho<EOS>(Skp, Tkp, fabs(__ldg(a.g.zt + k + 1)), drT_u, drS_u);
-            const double m = (double)a.maskT[c + 1];
-            drT_u *= m;
-            drS_u *= m;
+            eos_drho<EOS>(Sc, Tc, L1.pabs, drTc, drSc);
+            const bool m = a.maskT[c];
+            drTc = sel(m, drTc);
+            drSc = sel(m, drSc);
         }
         const double Kc = __ldg(a.K_iso + c);
-        const double dxu_[2] = {__ldg(a.g.dxu + i - 1), __ldg(a.g.dxu + i)};
-        const double facty[2] = {__ldg(a.g.cosu + j - 1) * __ldg(a.g.dyu + j - 1),
-                                 __ldg(a.g.cosu + j) * __ldg(a.g.dyu + j)};
-        double Ax[2][2], Ay[2][2];
-        double sumx = 0.0, sumy = 0.0;
-#pragma unroll
-        for (int kr = 0; kr < 2; ++kr) {
-            const double dT_ = kr ? drT_u : drT_c, dS_ = kr ? drS_u : drS_c;
-            const double drodzb = dT_ * dTz_c1 + dS_ * dSz_c1;
-            const double rden = 1.0 / (fmin(0.0, drodzb) - kEps);
-#pragma unroll
-            for (int ip = 0; ip < 2; ++ip) {
-                const double drodxb = dT_ * dTx[ip][kr] + dS_ * dSx[ip][kr];
-                const double sxb = -drodxb * rden;
-                const double taper = dm_taper(sxb, tp);
-                sumx += dxu_[ip] * Kc * taper * (sxb * sxb) * mWc1;
-                Ax[ip][kr] = taper * sxb * mWc1;
+        const double Kcm = __ldg(a.K_iso + c + km);
+        const double rdzt4 = L1.d4zt.ry;
+
+        // ---- east face: Ai_ez, K_11 (isoneutral.py:100-132) and flux_east (diffusion.py:25-47) ------
+        double Te = 0.0, Se = 0.0, Tpe = 0.0, Spe = 0.0;  // (i+1,j,k), (i+1,j,k+1)
+        if (inE || inT) {
+            Te = ld(T, ce);
+            Se = ld(S, ce);
+            Tpe = ld(T, ce + kp);
+            Spe = ld(S, ce + kp);
+        }
+        const double dTxc = Te - Tc, dSxc = Se - Sc;  // raw east differences at level k
+        const double mrdx = sel(a.maskU[c] != 0, Rj.cdxu.ry);
+        const double gTxc = dTxc * mrdx, gSxc = dSxc * mrdx;  // dTdx(i,j,k)
+        if (inE) {
+            const double Tme = ld(T, ce + km), Sme = ld(S, ce + km);
+            const double dT0e = Te - Tme, dS0e = Se - Sme, dT1e = Tpe - Te, dS1e = Spe - Se;
+            const bool mWe1 = hasKp && a.maskW[ce], mWe0 = hasKm && a.maskW[ce + km];
+            const double w1e = sel(mWe1, L1.rdzw), w0e = sel(mWe0, L0.rdzw);
+            double drTe, drSe;
+            if (Eos<EOS>::kExpensive) {
+                drTe = __ldg(a.drdT + ce);
+                drSe = __ldg(a.drdS + ce);
+            } else {
+                eos_drho<EOS>(Se, Te, L1.pabs, drTe, drSe);
+                const bool m = a.maskT[ce];
+                drTe = sel(m, drTe);
+                drSe = sel(m, drSe);
             }
+            const double Ke = __ldg(a.K_iso + ce), Kem = __ldg(a.K_iso + ce + km);
+            const double diffloc = hasKm ? 0.25 * (((Kc + Kcm) + Ke) + Kem) : 0.5 * (Kc + Ke);
+            const bool mU = a.maskU[c] != 0;
+            const double wz[2] = {sel(mU && hasKm, L0.dzw), sel(mU, L1.dzw)};  // dzw[k+kr-1] * maskU
+            const double gTz[2][2] = {{gTz0c, gTz1c}, {dT0e * w0e, dT1e * w1e}};  // [ip][kr]
+            const double gSz[2][2] = {{gSz0c, gSz1c}, {dS0e * w0e, dS1e * w1e}};
+            double A[2][2];
+            double sumz = 0.0;
 #pragma unroll
-            for (int jp = 0; jp < 2; ++jp) {
-                const double drodyb = dT_ * dTy[jp][kr] + dS_ * dSy[jp][kr];
-                const double syb = -drodyb * rden;
-                const double taper = dm_taper(syb, tp);
-                sumy += facty[jp] * Kc * taper * (syb * syb) * mWc1;
-                Ay[jp][kr] = taper * syb * mWc1;
+            for (int kr = 0; kr < 2; ++kr) {
+#pragma unroll
+                for (int ip = 0; ip < 2; ++ip) {
+                    const double dT_ = ip ? drTe : drTc, dS_ = ip ? drSe : drSc;
+                    const double drodxe = fma(dS_, gSxc, dT_ * gTxc);
+                    const double drodze = fma(dS_, gSz[ip][kr], dT_ * gTz[ip][kr]);
+                    const double sxe = -drodxe * rcp_fast(neg_part_minus_eps(drodze));
+                    const double tp = taper(sxe);
+                    sumz = fma(wz[kr], fmax(a.K_iso_steep, diffloc * tp), sumz);
+                    A[ip][kr] = tp * sxe;  // maskU is already in gTxc/gSxc
+                }
+            }
+            double* out = a.Ai_ez + c * 4;
+            if (hasKm) {
+                store_pair(out, A[0][0], A[0][1]);
+                store_pair(out + 2, A[1][0], A[1][1]);
+            } else {  // k = 0: the kr = 0 entries are never written (isoneutral.py:113-131, ki = 1)
+                out[1] = A[0][1];
+                out[3] = A[1][1];
+            }
+            const double K11 = sumz * rdzt4;
+            a.K_11[c] = K11;
+            if (FLUX) {
+                // at k = 0 the kr = 0 entries of Ai_ez keep their old values; they multiply a zero difference
+                const double A00 = hasKm ? A[0][0] : out[0], A10 = hasKm ? A[1][0] : out[2];
+                fl[0][0] = flux_face(diffloc, A00, A[0][1], A10, A[1][1], dT0c, dT1c, dT0e, dT1e, dTxc, L1.d4zt, Rj.cdxu, K11);
+                fl[1][0] = flux_face(diffloc, A00, A[0][1], A10, A[1][1], dS0c, dS1c, dS0e, dS1e, dSxc, L1.d4zt, Rj.cdxu, K11);
             }
         }
-        store_pair(a.Ai_bx + c * 4, Ax[0][0], Ax[0][1]);
-        store_pair(a.Ai_bx + c * 4 + 2, Ax[1][0], Ax[1][1]);
-        store_pair(a.Ai_by + c * 4, Ay[0][0], Ay[0][1]);
-        store_pair(a.Ai_by + c * 4 + 2, Ay[1][0], Ay[1][1]);
-        a.K_33[c] = sumx / (4.0 * __ldg(a.g.dxt + i)) +
-                    sumy / (4.0 * __ldg(a.g.dyt + j) * __ldg(a.g.cost + j));
+
+        // ---- north face: Ai_nz, K_22 (isoneutral.py:137-168) and flux_north (diffusion.py:52-77) ----
+        double Tn = 0.0, Sn = 0.0, Tpn = 0.0, Spn = 0.0;  // (i,j+1,k), (i,j+1,k+1)
+        if (inN || inT) {
+            Tn = ld(T, cn);
+            Sn = ld(S, cn);
+            Tpn = ld(T, cn + kp);
+            Spn = ld(S, cn + kp);
+        }
+        const double dTyc = Tn - Tc, dSyc = Sn - Sc;
+        const double mrdy = sel(a.maskV[c] != 0, Rj.dyu.ry);
+        const double gTyc = dTyc * mrdy, gSyc = dSyc * mrdy;  // dTdy(i,j,k)
+        if (inN) {
+            const double Tmn = ld(T, cn + km), Smn = ld(S, cn + km);
+            const double dT0n = Tn - Tmn, dS0n = Sn - Smn, dT1n = Tpn - Tn, dS1n = Spn - Sn;
+            const bool mWn1 = hasKp && a.maskW[cn], mWn0 = hasKm && a.maskW[cn + km];
+            const double w1n = sel(mWn1, L1.rdzw), w0n = sel(mWn0, L0.rdzw);
+            double drTn, drSn;
+            if (Eos<EOS>::kExpensive) {
+                drTn = __ldg(a.drdT + cn);
+                drSn = __ldg(a.drdS + cn);
+            } else {
+                eos_drho<EOS>(Sn, Tn, L1.pabs, drTn, drSn);
+                const bool m = a.maskT[cn];
+                drTn = sel(m, drTn);
+                drSn = sel(m, drSn);
+            }
+            const double Kn = __ldg(a.K_iso + cn), Knm = __ldg(a.K_iso + cn + km);
+            const double diffloc = hasKm ? 0.25 * (((Kc + Kcm) + Kn) + Knm) : 0.5 * (Kc + Kn);
+            const bool mV = a.maskV[c] != 0;
+            const double wz[2] = {sel(mV && hasKm, L0.dzw), sel(mV, L1.dzw)};
+            const double gTz[2][2] = {{gTz0c, gTz1c}, {dT0n * w0n, dT1n * w1n}};  // [jp][kr]
+            const double gSz[2][2] = {{gSz0c, gSz1c}, {dS0n * w0n, dS1n * w1n}};
+            double A[2][2];
+            double sumz = 0.0;
+#pragma unroll
+            for (int kr = 0; kr < 2; ++kr) {
+#pragma unroll
+                for (int jp = 0; jp < 2; ++jp) {
+                    const double dT_ = jp ? drTn : drTc, dS_ = jp ? drSn : drSc;
+                    const double drodyn = fma(dS_, gSyc, dT_ * gTyc);
+                    const double drodzn = fma(dS_, gSz[jp][kr], dT_ * gTz[jp][kr]);
+                    const double syn = -drodyn * rcp_fast(neg_part_minus_eps(drodzn));
+                    const double tp = taper(syn);
+                    sumz = fma(wz[kr], fmax(a.K_iso_steep, diffloc * tp), sumz);
+                    A[jp][kr] = tp * syn;
+                }
+            }
+            double* out = a.Ai_nz + c * 4;
+            if (hasKm) {
+                store_pair(out, A[0][0], A[0][1]);
+                store_pair(out + 2, A[1][0], A[1][1]);
+            } else {
+                out[1] = A[0][1];
+                out[3] = A[1][1];
+            }
+            const double K22 = sumz * rdzt4;
+            a.K_22[c] = K22;
+            if (FLUX) {
+                const double A00 = hasKm ? A[0][0] : out[0], A10 = hasKm ? A[1][0] : out[2];
+                fl[0][1] = strict::mul(Rj.cosu, flux_face(diffloc, A00, A[0][1], A10, A[1][1], dT0c, dT1c, dT0n, dT1n,
+                                                          dTyc, L1.d4zt, Rj.dyu, K22));
+                fl[1][1] = strict::mul(Rj.cosu, flux_face(diffloc, A00, A[0][1], A10, A[1][1], dS0c, dS1c, dS0n, dS1n,
+                                                          dSyc, L1.d4zt, Rj.dyu, K22));
+            }
+        }
+
+        // ---- top face: Ai_bx, Ai_by, K_33 (isoneutral.py:173-225) and flux_top (diffusion.py:85-111) --
+        if (inT) {
+            const RowTab Rs = row[j - 1 - jlo];
+            const double Tw = ld(T, cw), Sw = ld(S, cw), Tpw = ld(T, cw + 1), Spw = ld(S, cw + 1);
+            const double Ts = ld(T, cs), Ss = ld(S, cs), Tps = ld(T, cs + 1), Sps = ld(S, cs + 1);
+            // raw differences [ip|jp][kr]: tr(i+ip,j,k+kr) - tr(i-1+ip,j,k+kr) and the same in y
+            const double dTx[2][2] = {{Tc - Tw, Tp - Tpw}, {dTxc, Tpe - Tp}};
+            const double dSx[2][2] = {{Sc - Sw, Sp - Spw}, {dSxc, Spe - Sp}};
+            const double dTy[2][2] = {{Tc - Ts, Tp - Tps}, {dTyc, Tpn - Tp}};
+            const double dSy[2][2] = {{Sc - Ss, Sp - Sps}, {dSyc, Spn - Sp}};
+            // metric factors with the U/V masks folded in
+            const double mx[2][2] = {{sel(a.maskU[cw] != 0, Rj.r_cdxu_w), sel(a.maskU[cw + 1] != 0, Rj.r_cdxu_w)},
+                                     {mrdx, sel(a.maskU[c + 1] != 0, Rj.cdxu.ry)}};
+            const double my[2][2] = {{sel(a.maskV[cs] != 0, Rs.dyu.ry), sel(a.maskV[cs + 1] != 0, Rs.dyu.ry)},
+                                     {mrdy, sel(a.maskV[c + 1] != 0, Rj.dyu.ry)}};
+            double drTu, drSu;  // (i,j,k+1)
+            if (Eos<EOS>::kExpensive) {
+                drTu = __ldg(a.drdT + c + 1);
+                drSu = __ldg(a.drdS + c + 1);
+            } else {
+                eos_drho<EOS>(Sp, Tp, lev[k + 1].pabs, drTu, drSu);
+                const bool m = a.maskT[c + 1];
+                drTu = sel(m, drTu);
+                drSu = sel(m, drSu);
+            }
+            const double KcW = sel(mWc1, Kc);                                 // K_iso * maskW
+            const double cx[2] = {__ldg(a.g.dxu + i - 1) * KcW, __ldg(a.g.dxu + i) * KcW};
+            const double cy[2] = {Rs.facty * KcW, Rj.facty * KcW};
+            double Ax[2][2], Ay[2][2];
+            double sumx = 0.0, sumy = 0.0;
+#pragma unroll
+            for (int kr = 0; kr < 2; ++kr) {
+                const double dT_ = kr ? drTu : drTc, dS_ = kr ? drSu : drSc;
+                const double drodzb = fma(dS_, gSz1c, dT_ * gTz1c);
+                const double nrden = -rcp_fast(neg_part_minus_eps(drodzb));
+#pragma unroll
+                for (int ip = 0; ip < 2; ++ip) {
+                    const double drodxb = fma(dS_, dSx[ip][kr] * mx[ip][kr], dT_ * (dTx[ip][kr] * mx[ip][kr]));
+                    const double sxb = drodxb * nrden;
+                    const double tp = taper(sxb);
+                    const double ts = tp * sxb;
+                    sumx = fma(cx[ip], ts * sxb, sumx);
+                    Ax[ip][kr] = sel(mWc1, ts);
+                }
+#pragma unroll
+                for (int jp = 0; jp < 2; ++jp) {
+                    const double drodyb = fma(dS_, dSy[jp][kr] * my[jp][kr], dT_ * (dTy[jp][kr] * my[jp][kr]));
+                    const double syb = drodyb * nrden;
+                    const double tp = taper(syb);
+                    const double ts = tp * syb;
+                    sumy = fma(cy[jp], ts * syb, sumy);
+                    Ay[jp][kr] = sel(mWc1, ts);
+                }
+            }
+            store_pair(a.Ai_bx + c * 4, Ax[0][0], Ax[0][1]);
+            store_pair(a.Ai_bx + c * 4 + 2, Ax[1][0], Ax[1][1]);
+            store_pair(a.Ai_by + c * 4, Ay[0][0], Ay[0][1]);
+            store_pair(a.Ai_by + c * 4 + 2, Ay[1][0], Ay[1][1]);
+            a.K_33[c] = fma(sumx, d4xt[0].ry, sumy * Rj.d4ytc.ry);
+            if (FLUX) {
+                fl[0][2] = flux_top(Kc, Ax, Ay, dTx, dTy, Rs.cosu, Rj.cosu, Rj.cost, d4xt[0], Rj.d4ytc);
+                fl[1][2] = flux_top(Kc, Ax, Ay, dSx, dSy, Rs.cosu, Rj.cosu, Rj.cost, d4xt[0], Rj.d4ytc);
+            }
+        }
     }
+    if (FLUX) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int f = 0; f < 3; ++f) a.flux[t][f][c] = fl[t][f];
+    }
+}
+
+size_t pre_smem_bytes(int nz) {
+    const int jr = kPreBlock / nz + 3;
+    return 64 * 8 + (size_t)nz * sizeof(LevTab) + (size_t)jr * sizeof(RowTab) + sizeof(Divisor);
+}
+
+template <int EOS>
+static void launch_pre_eos(cudaStream_t s, const PreArgs& a, dim3 grid, size_t smem) {
+    if (a.with_flux)
+        iso_pre_kernel<EOS, true><<<grid, kPreBlock, smem, s>>>(a);
+    else
+        iso_pre_kernel<EOS, false><<<grid, kPreBlock, smem, s>>>(a);
 }
 
 void launch_iso_pre(cudaStream_t s, const PreArgs& a) {
@@ -322,14 +462,14 @@ void launch_iso_pre(cudaStream_t s, const PreArgs& a) {
         count_launch();
         if (!check_launch("eos5_kernel")) return;
     }
-    const int block = 128;
-    dim3 grid((M * nz + block - 1) / block, N);
+    dim3 grid((M * nz + kPreBlock - 1) / kPreBlock, N);
+    const size_t smem = pre_smem_bytes(nz);
     switch (a.eos) {
-    case 1: iso_pre_kernel<1><<<grid, block, 0, s>>>(a); break;
-    case 2: iso_pre_kernel<2><<<grid, block, 0, s>>>(a); break;
-    case 3: iso_pre_kernel<3><<<grid, block, 0, s>>>(a); break;
-    case 4: iso_pre_kernel<4><<<grid, block, 0, s>>>(a); break;
-    default: iso_pre_kernel<5><<<grid, block, 0, s>>>(a); break;
+    case 1: launch_pre_eos<1>(s, a, grid, smem); break;
+    case 2: launch_pre_eos<2>(s, a, grid, smem); break;
+    case 3: launch_pre_eos<3>(s, a, grid, smem); break;
+    case 4: launch_pre_eos<4>(s, a, grid, smem); break;
+    default: launch_pre_eos<5>(s, a, grid, smem); break;
     }
     count_launch();
     check_launch("iso_pre_kernel");

@@ -1,0 +1,76 @@
+"""x-slab domain decomposition and the 2-cell halo exchange of the tracers.
+
+Mirrors the reference's convention for ``num_proc = (P, 1)`` (veros/distributed.py:111-215,
+veros/variables.py:138-149): rank r owns interior columns [r*nx/P, (r+1)*nx/P) and stores them with
+two ghost columns per side; with ``enable_cyclic_x`` the ranks form a ring (distributed.py:179-196).
+Because x is the slowest axis of the C-ordered arrays, the halos ``arr[2:4]`` / ``arr[-4:-2]`` are
+contiguous blocks: no packing kernel is needed for 3-D fields.
+
+The exchange itself replaces ``exchange_overlap`` (distributed.py:218-326) for the west/east
+directions, the only ones a (P, 1) decomposition has: one batched NCCL send/recv pair per neighbour
+(``torch.distributed.batch_isend_irecv`` = ncclGroupStart/ncclSend/ncclRecv/ncclGroupEnd).  With the
+gloo backend the same code runs on CPU tensors (used by the world_size-2 tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def slab_bounds(nx_global, world_size, rank):
+    """Interior x-range [x0, x1) of `rank` (even division required, as distributed.py:124-128)."""
+    if nx_global % world_size:
+        raise ValueError(f"nx={nx_global} is not divisible by the number of slabs {world_size}")
+    n = nx_global // world_size
+    return rank * n, (rank + 1) * n
+
+
+def neighbours(rank, world_size, cyclic):
+    west = rank - 1 if rank > 0 else (world_size - 1 if cyclic else None)
+    east = rank + 1 if rank < world_size - 1 else (0 if cyclic else None)
+    return west, east
+
+
+def exchange_halos_x(fields, cyclic=True, group=None, level=None):
+    """In place: fill the ghost columns arr[:2] and arr[-2:] of every tensor in `fields` from the
+    neighbouring slabs' interior edges arr[-4:-2] / arr[2:4].  First axis of every field is x.
+    `level` selects one time level of (N, M, nz, 3) tracers (what thermodynamics.py:293-298 exchanges);
+    the strided halo is then staged through a small contiguous buffer."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def view(f, sl):
+        return f[sl] if level is None else f[sl][..., level]
+
+    if world == 1:
+        if cyclic:
+            for f in fields:
+                view(f, slice(-2, None)).copy_(view(f, slice(2, 4)))
+                view(f, slice(0, 2)).copy_(view(f, slice(-4, -2)))
+        return
+    west, east = neighbours(rank, world, cyclic)
+    sends, recvs, unpack = [], [], []
+    # Order matters when west == east (two slabs on a ring): NCCL matches the messages of a peer pair
+    # in posting order, so every rank posts east-going sends first and west-ghost receives first.
+    for f in fields:
+        if east is not None:
+            sends.append(dist.P2POp(dist.isend, view(f, slice(-4, -2)).contiguous(), east, group))
+    for f in fields:
+        if west is not None:
+            sends.append(dist.P2POp(dist.isend, view(f, slice(2, 4)).contiguous(), west, group))
+    for f in fields:
+        if west is not None:
+            dst = view(f, slice(0, 2))
+            buf = dst if dst.is_contiguous() else torch.empty_like(dst, memory_format=torch.contiguous_format)
+            recvs.append(dist.P2POp(dist.irecv, buf, west, group))
+            unpack.append((dst, buf))
+    for f in fields:
+        if east is not None:
+            dst = view(f, slice(-2, None))
+            buf = dst if dst.is_contiguous() else torch.empty_like(dst, memory_format=torch.contiguous_format)
+            recvs.append(dist.P2POp(dist.irecv, buf, east, group))
+            unpack.append((dst, buf))
+    if sends or recvs:
+        for w in dist.batch_isend_irecv(sends + recvs):
+            w.wait()
+    for dst, buf in unpack:
+        if dst is not buf:
+            dst.copy_(buf)
