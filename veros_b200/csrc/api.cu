@@ -83,7 +83,8 @@ static Grid make_grid(const VerosB200IsoDescriptor* d, void* dxt, void* dxu, voi
 }
 
 static size_t pre_ws_doubles(const VerosB200IsoDescriptor* d) {
-    return d->eq_of_state_type == 5 ? (size_t)2 * d->nx_tot * d->ny_tot * d->nz : 0;
+    const size_t tabs = (pre_tables_doubles(d->nx_tot, d->ny_tot, d->nz) + 1) & ~(size_t)1;  // keep 16 B alignment
+    return tabs + (d->eq_of_state_type == 5 ? (size_t)2 * d->nx_tot * d->ny_tot * d->nz : 0);
 }
 
 }  // namespace vb
@@ -140,7 +141,8 @@ void veros_b200_iso_pre_f64(void* stream, void** B, const char* opaque, size_t l
     a.K_11 = (double*)B[28];
     a.K_22 = (double*)B[29];
     a.K_33 = (double*)B[30];
-    a.drdT = (double*)B[31];
+    a.tables = (double*)B[31];
+    a.drdT = a.tables + ((pre_tables_doubles(d->nx_tot, d->ny_tot, d->nz) + 1) & ~(size_t)1);
     a.drdS = a.drdT + n3;
     a.with_flux = 0;
     for (int t = 0; t < 2; ++t)
@@ -219,8 +221,9 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     p.K_11 = (double*)B[40];
     p.K_22 = (double*)B[41];
     p.K_33 = (double*)B[42];
-    p.drdT = ws + 6 * n3;  // behind the six flux arrays
-    p.drdS = ws + 7 * n3;
+    p.tables = ws + 8 * n3;  // behind the six flux and two dissipation arrays
+    p.drdT = p.tables + ((pre_tables_doubles(d->nx_tot, d->ny_tot, d->nz) + 1) & ~(size_t)1);
+    p.drdS = p.drdT + n3;
     p.with_flux = 1;
     for (int t = 0; t < 2; ++t)
         for (int q = 0; q < 3; ++q) p.flux[t][q] = ws + (size_t)(3 * t + q) * n3;

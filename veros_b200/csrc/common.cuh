@@ -29,6 +29,8 @@ struct PreArgs {
     const uint8_t *maskT, *maskU, *maskV, *maskW;
     double *Ai_ez, *Ai_nz, *Ai_bx, *Ai_by, *K_11, *K_22, *K_33;
     double *drdT, *drdS;  // workspace, EOS 5 only
+    double* tables;       // workspace, pre_tables_doubles() doubles: metric tables built per call
+    double two_rd, m2c0, s_max;  // taper constants (filled by launch_iso_pre)
     double* flux[2][3];   // [temp|salt][east|north|top] outputs when with_flux
     int with_flux;
     int eos;
@@ -58,6 +60,7 @@ struct DiffArgs {
 
 // ---- launchers (one per translation unit) -----------------------------------------------------
 void launch_iso_pre(cudaStream_t s, const PreArgs& a);
+size_t pre_tables_doubles(int N, int M, int nz);
 size_t diffusion_workspace_doubles(int N, int M, int nz, int ntr);
 void launch_iso_diffusion_ws(cudaStream_t s, const DiffArgs& a, double* workspace);
 void launch_solve_implicit(cudaStream_t s, int ncol, int nz, const double* a, const double* b, const double* c,

@@ -162,6 +162,7 @@ flux_kernel(const DiffArgs a, const int t, double* __restrict__ flux_east, doubl
 // ------------------------------------------------------------------------------------------------
 struct Scratch {
     const double *fe[2], *fn[2], *ft[2];
+    double* diss[2];  // T-point dissipation of each tracer (ENERGY only)
 };
 
 constexpr int kUpdBlock = 128;
@@ -211,51 +212,81 @@ update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch
     const bool i_int = (i >= 2 && i < N - 2);
 
     // ---- phase B --------------------------------------------------------------------------------
-    if (i_int) {
-        for (int idx = threadIdx.x; idx < ncells; idx += kUpdBlock) {
-            const int q = idx / nz, k = idx - q * nz;
-            const int j = j0 + q;
-            if (j < 2 || j >= M - 2) continue;
-            const size_t c = base + idx;
-            const int s = q * pitch + k;
-            const double mT = (double)a.maskT[c];
+    // Every global load of a (cell, tracer) pair is issued before the first dependent store: the
+    // compiler must keep loads behind earlier stores that might alias, so interleaving them would
+    // serialise four memory round trips per cell.
+    for (int idx = threadIdx.x; idx < ncells; idx += kUpdBlock) {
+        const int q = idx / nz, k = idx - q * nz;
+        const int j = j0 + q;
+        const bool interior = i_int && j >= 2 && j < M - 2;
+        if (!interior && !ENERGY) continue;
+        const size_t c = base + idx;
+        const int s = q * pitch + k;
+        const double mT = interior ? (double)a.maskT[c] : 0.0;
+        double k33 = 0.0, k33m = 0.0;
+        if (!SKEW && interior) {
+            k33 = (k < nz - 1) ? __ldg(a.K_33 + c) : 0.0;
+            k33m = (k > 0) ? __ldg(a.K_33 + c - 1) : 0.0;
+        }
 #pragma unroll
-            for (int t = 0; t < NTR; ++t) {
-                const double fe_c = __ldg(f.fe[t] + c), fe_w = __ldg(f.fe[t] + c - plane);
-                const double fn_c = __ldg(f.fn[t] + c), fn_s = __ldg(f.fn[t] + c - nz);
-                const double ft_c = __ldg(f.ft[t] + c);
-                const double ft_m = k > 0 ? __ldg(f.ft[t] + c - 1) : 0.0;
+        for (int t = 0; t < NTR; ++t) {
+            // loads
+            const double fe_c = __ldg(f.fe[t] + c), fe_w = __ldg(f.fe[t] + c - plane);
+            const double fn_c = __ldg(f.fn[t] + c), fn_s = __ldg(f.fn[t] + c - nz);
+            double ft_c = 0.0, ft_m = 0.0, dtr_old = 0.0, tr_old = 0.0;
+            if (interior) {
+                ft_c = __ldg(f.ft[t] + c);
+                ft_m = k > 0 ? __ldg(f.ft[t] + c - 1) : 0.0;
+                dtr_old = a.t[t].dtracer[c];
+                tr_old = a.t[t].tr[c * 3 + taup1];
+            }
+            double xc = 0.0, xe = 0.0, xw = 0.0, xn = 0.0, xs = 0.0;
+            if (ENERGY) {
+                const double* __restrict__ X = a.t[t].int_drhodX + tau;
+                xc = ldt(X, c);
+                xe = ldt(X, c + plane);
+                xw = ldt(X, c - plane);
+                xn = ldt(X, c + nz);
+                xs = ldt(X, c - nz);
+            }
+            // arithmetic + stores
+            if (interior) {
                 double e = mul(mT, add(strict::div(sub(fe_c, fe_w), dcdxt[q]), strict::div(sub(fn_c, fn_s), dcdyt[q])));
                 if (k == 0)
                     e = add(e, strict::div(mul(mT, ft_c), ddzt[0]));
                 else
                     e = add(e, strict::div(mul(mT, sub(ft_c, ft_m)), ddzt[k]));
-                a.t[t].dtracer[c] = add(a.t[t].dtracer[c], e);              // diffusion.py:196
-                const double v = add(a.t[t].tr[c * 3 + taup1], mul(dt, e));  // diffusion.py:197
+                a.t[t].dtracer[c] = add(dtr_old, e);        // diffusion.py:196
+                const double v = add(tr_old, mul(dt, e));  // diffusion.py:197
                 a.t[t].tr[c * 3 + taup1] = v;
                 if (!SKEW) R[t][s] = v;
             }
-            if (!SKEW) {  // _calc_implicit_part, diffusion.py:149-164
-                const int ks = ksv[q];
-                const double del = (k < nz - 1) ? mul(dt_dzw[k], __ldg(a.K_33 + c)) : 0.0;
-                const double delm = (k > 0) ? mul(dt_dzw[k - 1], __ldg(a.K_33 + c - 1)) : 0.0;
-                double b;
-                if (k == ks)
-                    b = add(1.0, strict::div(del, ddzt[k]));  // b_tri_edge
-                else if (k == nz - 1)
-                    b = add(1.0, strict::div(delm, ddzt[k]));
-                else
-                    b = add(1.0, strict::div(add(del, delm), ddzt[k]));
-                D[s] = b;
-                U[s] = (k < nz - 1) ? strict::div(-del, ddzt[k]) : 0.0;
-                if (k > 0) L[s - 1] = (k > ks) ? strict::div(-delm, ddzt[k]) : 0.0;
+            if (ENERGY) {  // compute_dissipation, veros/core/diffusion.py:15-35 (on [1:-1, 1:-1])
+                const double gx = add(mul(sub(xe, xc), fe_c), mul(sub(xc, xw), fe_w));
+                const double gy = add(mul(sub(xn, xc), fn_c), mul(sub(xc, xs), fn_s));
+                f.diss[t][c] = add(strict::div(mul(fac_diss, gx), dcdxt[q]), strict::div(mul(fac_diss, gy), dcdyt[q]));
             }
         }
+        if (!SKEW && interior) {  // _calc_implicit_part, diffusion.py:149-164
+            const int ks = ksv[q];
+            const double del = (k < nz - 1) ? mul(dt_dzw[k], k33) : 0.0;
+            const double delm = (k > 0) ? mul(dt_dzw[k - 1], k33m) : 0.0;
+            double b;
+            if (k == ks)
+                b = add(1.0, strict::div(del, ddzt[k]));  // b_tri_edge
+            else if (k == nz - 1)
+                b = add(1.0, strict::div(delm, ddzt[k]));
+            else
+                b = add(1.0, strict::div(add(del, delm), ddzt[k]));
+            D[s] = b;
+            U[s] = (k < nz - 1) ? strict::div(-del, ddzt[k]) : 0.0;
+            if (k > 0) L[s - 1] = (k > ks) ? strict::div(-delm, ddzt[k]) : 0.0;
+        }
     }
+    __syncthreads();  // also orders this CTA's diss[] stores before the phase D loads of its own cells
 
     // ---- phase C: one thread per water column, dgtsv on all right-hand sides ----------------------
     if (!SKEW) {
-        __syncthreads();
         if (i_int) {
             for (int q = threadIdx.x; q < ncols; q += kUpdBlock) {
                 const int j = j0 + q;
@@ -278,58 +309,66 @@ update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch
         const bool interior = i_int && j >= 2 && j < M - 2;
         const int ks = ksv[q];
         const bool land = ks >= 0;
-        double P = 0.0;
-        if (ENERGY) P = a.P_diss[c];
+        const bool up = k < nz - 1;
+        const bool solved = !SKEW && interior && land && k >= ks;
+        if (!ENERGY && !solved) continue;
+        // loads
+        double P = 0.0, k33 = 0.0, mW = 0.0;
+        double old[NTR], dtr_mid[NTR], d0[NTR], d1[NTR], x0[NTR], x1[NTR], ftc[NTR];
+        if (ENERGY) {
+            P = a.P_diss[c];
+            if (interior && up) {
+                k33 = __ldg(a.K_33 + c);
+                mW = (double)a.maskW[c];
+            }
+        }
 #pragma unroll
         for (int t = 0; t < NTR; ++t) {
-            if (!SKEW && interior && land && k >= ks) {  // where(water_mask, sol, tr); diffusion.py:168,203-204
-                const double old = a.t[t].tr[c * 3 + taup1];
+            old[t] = dtr_mid[t] = d0[t] = d1[t] = x0[t] = x1[t] = ftc[t] = 0.0;
+            if (solved) {
+                old[t] = a.t[t].tr[c * 3 + taup1];
+                dtr_mid[t] = a.t[t].dtracer[c];
+            }
+            if (ENERGY) {
+                d0[t] = f.diss[t][c];
+                if (up) d1[t] = f.diss[t][c + 1];
+                if (interior && up) {
+                    const double* __restrict__ X = a.t[t].int_drhodX + tau;
+                    x0[t] = ldt(X, c);
+                    x1[t] = ldt(X, c + 1);
+                    ftc[t] = __ldg(f.ft[t] + c);
+                }
+            }
+        }
+        // arithmetic + stores
+#pragma unroll
+        for (int t = 0; t < NTR; ++t) {
+            if (solved) {  // where(water_mask, sol, tr); diffusion.py:168,203-204
                 const double nw = R[t][s];
-                a.t[t].dtracer[c] = add(a.t[t].dtracer[c], strict::div(sub(nw, old), ddt));
+                a.t[t].dtracer[c] = add(dtr_mid[t], strict::div(sub(nw, old[t]), ddt));
                 a.t[t].tr[c * 3 + taup1] = nw;
             }
             if (ENERGY) {
-                // compute_dissipation (veros/core/diffusion.py:15-35) at levels k and k+1 of this column
-                const double* __restrict__ X = a.t[t].int_drhodX + tau;
-                const bool up = k < nz - 1;
-                double dk[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (u == 1 && !up) {
-                        dk[1] = 0.0;
-                        break;
-                    }
-                    const size_t cc = c + u;
-                    const double xc = ldt(X, cc);
-                    const double fe_c = __ldg(f.fe[t] + cc), fe_w = __ldg(f.fe[t] + cc - plane);
-                    const double fn_c = __ldg(f.fn[t] + cc), fn_s = __ldg(f.fn[t] + cc - nz);
-                    const double gx = add(mul(sub(ldt(X, cc + plane), xc), fe_c), mul(sub(xc, ldt(X, cc - plane)), fe_w));
-                    const double gy = add(mul(sub(ldt(X, cc + nz), xc), fn_c), mul(sub(xc, ldt(X, cc - nz)), fn_s));
-                    dk[u] = add(strict::div(mul(fac_diss, gx), dcdxt[q]), strict::div(mul(fac_diss, gy), dcdyt[q]));
-                }
                 // dissipation_on_wgrid, veros/core/diffusion.py:41-62
                 double dw;
                 if (up) {
-                    const double m = mul(0.5, add(dk[0], dk[1]));
+                    const double m = mul(0.5, add(d0[t], d1[t]));
                     const double edge = (land && k == ks) ? 1.0 : 0.0, water = (land && k > ks) ? 1.0 : 0.0;
-                    const double dzw_pad = a.g.dzw[k > 0 ? k - 1 : 0];
-                    dw = add(mul(add(m, mul(0.5, strict::div(mul(dk[0], dzw_pad), ddzw[k]))), edge), mul(m, water));
+                    const double dzw_pad = ddzw[k > 0 ? k - 1 : 0].y;
+                    dw = add(mul(add(m, mul(0.5, strict::div(mul(d0[t], dzw_pad), ddzw[k]))), edge), mul(m, water));
                 } else {
-                    dw = mul(dk[0], land ? 1.0 : 0.0);
+                    dw = mul(d0[t], land ? 1.0 : 0.0);
                 }
                 P = add(P, dw);  // diffusion.py:246-249
                 if (interior && up) {  // diffusion.py:254-279
-                    const double fxa = strict::div(add(-ldt(X, c + 1), ldt(X, c)), ddzw[k]);
-                    const double mW = (double)a.maskW[c];
-                    const double ft_c = __ldg(f.ft[t] + c);
+                    const double fxa = strict::div(add(-x1[t], x0[t]), ddzw[k]);
                     double v;
                     if (SKEW) {
-                        v = mul(mul(mul(gr, fxa), ft_c), mW);
+                        v = mul(mul(mul(gr, fxa), ftc[t]), mW);
                     } else {
                         // tr[taup1] after the update: R holds it for every interior cell of the tile
                         const double dtr = sub(R[t][s + 1], R[t][s]);
-                        v = mul(mul(gr, fxa),
-                                add(mul(ft_c, mW), mul(strict::div(mul(__ldg(a.K_33 + c), dtr), ddzw[k]), mW)));
+                        v = mul(mul(gr, fxa), add(mul(ftc[t], mW), mul(strict::div(mul(k33, dtr), ddzw[k]), mW)));
                     }
                     P = add(P, v);
                 }
@@ -371,14 +410,17 @@ void launch_update(cudaStream_t s, const DiffArgs& a, const Scratch& f) {
 
 }  // namespace
 
-// workspace layout (doubles): per tracer flux_east, flux_north, flux_top, each N*M*nz
-size_t diffusion_workspace_doubles(int N, int M, int nz, int ntr) { return (size_t)3 * ntr * N * M * nz; }
+// workspace layout (doubles): per tracer flux_east, flux_north, flux_top (3*ntr arrays of N*M*nz),
+// then one dissipation array per tracer
+size_t diffusion_workspace_doubles(int N, int M, int nz, int ntr) { return (size_t)4 * ntr * N * M * nz; }
 
 void launch_iso_diffusion_ws(cudaStream_t s, const DiffArgs& a, double* ws) {
     const int N = a.g.N, M = a.g.M, nz = a.g.nz;
     if (N < 5 || M < 5 || nz < 2) return;
     const size_t n3 = (size_t)N * M * nz;
     Scratch f;
+    f.diss[0] = ws + (size_t)(3 * a.ntr) * n3;
+    f.diss[1] = f.diss[0] + (a.ntr > 1 ? n3 : 0);
     for (int t = 0; t < a.ntr; ++t) {
         double* fe = ws + (size_t)(3 * t) * n3;
         double* fn = fe + n3;

@@ -34,7 +34,7 @@ using strict::make_divisor;
 
 constexpr double kEps = 1e-20;  // isoneutral.py:28
 
-__constant__ double c_exp2_table[64] = {
+__device__ const double g_exp2_table[64] = {
     0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
     0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
     0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
@@ -63,7 +63,7 @@ __device__ __forceinline__ double rcp_fast(double x) {
 
 // exp(u) for u in [-700, 700], relative error < 4e-16, no branches.
 //   u = (64 n + j) ln2/64 + r,  exp(u) = 2^n * 2^(j/64) * (1 + r q(r)),  |r| <= ln2/128
-__device__ __forceinline__ double exp_fast(double u, const double* __restrict__ tab) {
+__device__ __forceinline__ double exp_fast(double u) {
     constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer in the low word
     double t = fma(u, 0x1.71547652b82fep+6, kMagic);
     const int ni = __double2loint(t);
@@ -75,7 +75,7 @@ __device__ __forceinline__ double exp_fast(double u, const double* __restrict__ 
     q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
     const double p = r * q;
-    const double T = tab[ni & 63];
+    const double T = __ldg(&g_exp2_table[ni & 63]);
     const double e = fma(T, p, T);
     return __hiloint2double(__double2hiint(e) + ((ni >> 6) << 20), __double2loint(e));
 }
@@ -84,14 +84,13 @@ struct Taper {
     double two_rd;   // 2 / iso_dslope
     double m2c0;     // -2 iso_slopec / iso_dslope
     double s_max;    // |s| beyond which exp(-2x) would overflow; the taper is exactly 0 there anyway
-    const double* tab;
     // dm_taper (isoneutral.py:10-15): 0.5*(1+tanh(x)), x = (slopec-|s|)/dslope, as 1/(1+exp(-2x)).
     // "2q - 1" is rounded like a tanh value, so 1 + tanh(x) quantises to multiples of 2^-53 near -1
     // exactly as the reference's does (the taper is exactly 0 for x < -18.4).
     __device__ __forceinline__ double operator()(double s) const {
         const double sa = fmin(fabs(s), s_max);
         const double u = fma(sa, two_rd, m2c0);
-        const double e = exp_fast(u, tab);
+        const double e = exp_fast(u);
         const double q = rcp_fast(1.0 + e);
         const double th = fma(2.0, q, -1.0);
         return fma(0.5, th, 0.5);
@@ -124,64 +123,102 @@ eos5_kernel(size_t ncell, int nz, const double* __restrict__ temp, const double*
     drdS[c] = dS;
 }
 
-// Shared-memory tables of one CTA (plane i, flattened cells [p0, p0 + blockDim)):
-//   per level k:  d4zt = 4 dzt[k] (+ reciprocal), rdzw = 1/dzw[k], dzw[k], |zt[k]|
-//   per row j in [jlo-1, jhi]:  cost*dxu[i], 1/(cost*dxu[i-1]), dyu, cost, (4 dyt) cost (+ reciprocals),
-//                               cosu, cosu*dyu
+// Metric tables, built once per call by setup_kernel in the workspace (a few KB, L1/L2 resident):
+//   LevTab[nz]   4 dzt[k] (+ correctly rounded reciprocal), 1/dzw[k], dzw[k], |zt[k]|
+//   RowTab[M]    dyu, cost, (4 dyt) cost (+ reciprocals), cosu, cosu*dyu
+//   XTab[N]      4 dxt[i] (+ reciprocal), dxu[i]
+//   Cdxu[N][M]   cost[j]*dxu[i] (+ reciprocal)
+// No per-thread division by a grid metric remains in the main kernel.
 struct RowTab {
-    Divisor cdxu, dyu, cost, d4ytc;
-    double r_cdxu_w, cosu, facty, pad;
+    Divisor dyu, cost, d4ytc;
+    double cosu, facty;
 };
 struct LevTab {
     Divisor d4zt;
     double rdzw, dzw, pabs, pad;
 };
+struct XTab {
+    Divisor d4xt;
+    double dxu, pad;
+};
+struct Tables {
+    const LevTab* lev;
+    const RowTab* row;
+    const XTab* xt;
+    const Divisor* cdxu;
+};
+
+__host__ __device__ inline size_t tables_doubles(int N, int M, int nz) {
+    return (size_t)nz * (sizeof(LevTab) / 8) + (size_t)M * (sizeof(RowTab) / 8) + (size_t)N * (sizeof(XTab) / 8) +
+           (size_t)N * M * (sizeof(Divisor) / 8);
+}
+
+__host__ __device__ inline Tables tables_at(double* base, int N, int M, int nz) {
+    Tables t;
+    LevTab* lev = reinterpret_cast<LevTab*>(base);
+    RowTab* row = reinterpret_cast<RowTab*>(lev + nz);
+    XTab* xt = reinterpret_cast<XTab*>(row + M);
+    Divisor* cd = reinterpret_cast<Divisor*>(xt + N);
+    (void)N;
+    t.lev = lev;
+    t.row = row;
+    t.xt = xt;
+    t.cdxu = cd;
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+setup_kernel(const Grid g, double* base) {
+    const int N = g.N, M = g.M, nz = g.nz;
+    const Tables t = tables_at(base, N, M, nz);
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nth = gridDim.x * blockDim.x;
+    for (int k = tid; k < nz; k += nth) {
+        LevTab e;
+        e.d4zt = make_divisor(4.0 * g.dzt[k]);
+        e.dzw = g.dzw[k];
+        e.rdzw = 1.0 / e.dzw;
+        e.pabs = fabs(g.zt[k]);
+        e.pad = 0.0;
+        const_cast<LevTab*>(t.lev)[k] = e;
+    }
+    for (int j = tid; j < M; j += nth) {
+        RowTab e;
+        const double cost = g.cost[j], dyu = g.dyu[j], cosu = g.cosu[j];
+        e.dyu = make_divisor(dyu);
+        e.cost = make_divisor(cost);
+        e.d4ytc = make_divisor(4.0 * g.dyt[j] * cost);
+        e.cosu = cosu;
+        e.facty = cosu * dyu;
+        const_cast<RowTab*>(t.row)[j] = e;
+    }
+    for (int i = tid; i < N; i += nth) {
+        XTab e;
+        e.d4xt = make_divisor(4.0 * g.dxt[i]);
+        e.dxu = g.dxu[i];
+        e.pad = 0.0;
+        const_cast<XTab*>(t.xt)[i] = e;
+    }
+    for (int q = tid; q < N * M; q += nth) {
+        const int i = q / M, j = q - i * M;
+        const_cast<Divisor*>(t.cdxu)[q] = make_divisor(g.cost[j] * g.dxu[i]);
+    }
+}
+
+__device__ __forceinline__ Divisor ld_div(const Divisor* p) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    return Divisor{v.x, v.y};
+}
 
 constexpr int kPreBlock = 128;
 
 template <int EOS, bool FLUX>
 __global__ void __launch_bounds__(kPreBlock)
 iso_pre_kernel(const PreArgs a) {
-    extern __shared__ double sm[];
     const int N = a.g.N, M = a.g.M, nz = a.g.nz;
     const int i = blockIdx.y;
     const int p0 = blockIdx.x * kPreBlock;
-    const int jlo = max(p0 / nz - 1, 0);
-    const int jhi = min(M - 1, (p0 + kPreBlock - 1) / nz);
-    const int jr = jhi - jlo + 1;
-
-    double* tab = sm;                                        // 64 doubles
-    LevTab* lev = reinterpret_cast<LevTab*>(tab + 64);       // nz
-    RowTab* row = reinterpret_cast<RowTab*>(lev + nz);       // jr
-    Divisor* d4xt = reinterpret_cast<Divisor*>(row + jr);    // 1
-    const int iw = max(i - 1, 0);
-    if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_table[threadIdx.x];
-    if (threadIdx.x == 64) d4xt[0] = make_divisor(4.0 * a.g.dxt[i]);
-    for (int k = threadIdx.x; k < nz; k += kPreBlock) {
-        LevTab t;
-        t.d4zt = make_divisor(4.0 * a.g.dzt[k]);
-        t.dzw = a.g.dzw[k];
-        t.rdzw = 1.0 / t.dzw;
-        t.pabs = fabs(a.g.zt[k]);
-        t.pad = 0.0;
-        lev[k] = t;
-    }
-    for (int q = threadIdx.x; q < jr; q += kPreBlock) {
-        const int j = jlo + q;
-        RowTab t;
-        const double cost = a.g.cost[j], dyu = a.g.dyu[j], cosu = a.g.cosu[j];
-        t.cdxu = make_divisor(cost * a.g.dxu[i]);
-        t.r_cdxu_w = 1.0 / (a.g.dxu[iw] * cost);
-        t.dyu = make_divisor(dyu);
-        t.cost = make_divisor(cost);
-        t.d4ytc = make_divisor(4.0 * a.g.dyt[j] * cost);
-        t.cosu = cosu;
-        t.facty = cosu * dyu;
-        t.pad = 0.0;
-        row[q] = t;
-    }
-    __syncthreads();
-
+    const Tables tb = tables_at(a.tables, N, M, nz);
     const int p = p0 + threadIdx.x;
     if (p >= M * nz) return;
     const int j = p / nz;
@@ -204,11 +241,29 @@ iso_pre_kernel(const PreArgs a) {
         const bool hasKm = k >= 1, hasKp = k < nz - 1;
         const int km = hasKm ? -1 : 0, kp = hasKp ? 1 : 0;  // clamped neighbours (pad_z_edges)
         const size_t ce = c + plane, cn = c + nz, cw = c - plane, cs = c - nz;
-        const LevTab L1 = lev[k];
-        const LevTab L0 = lev[k + km];
-        const RowTab Rj = row[j - jlo];
-        const Taper taper = {2.0 / a.iso_dslope, -2.0 * a.iso_slopec / a.iso_dslope,
-                             (345.0 + a.iso_slopec / a.iso_dslope) * a.iso_dslope, tab};
+        // metric table entries of this level / row / plane (read-only path, L1 resident)
+        struct { Divisor d4zt; double rdzw, dzw, pabs; } L1, L0;
+        {
+            const LevTab* l1 = tb.lev + k;
+            const LevTab* l0 = tb.lev + k + km;
+            L1.d4zt = ld_div(&l1->d4zt);
+            const double2 a1 = __ldg(reinterpret_cast<const double2*>(&l1->rdzw));
+            L1.rdzw = a1.x; L1.dzw = a1.y; L1.pabs = __ldg(&l1->pabs);
+            const double2 a0 = __ldg(reinterpret_cast<const double2*>(&l0->rdzw));
+            L0.rdzw = a0.x; L0.dzw = a0.y; L0.pabs = 0.0; L0.d4zt = L1.d4zt;
+        }
+        struct { Divisor cdxu, dyu, cost, d4ytc; double cosu, facty; } Rj;
+        {
+            const RowTab* r = tb.row + j;
+            Rj.dyu = ld_div(&r->dyu);
+            Rj.cost = ld_div(&r->cost);
+            Rj.d4ytc = ld_div(&r->d4ytc);
+            const double2 cf = __ldg(reinterpret_cast<const double2*>(&r->cosu));
+            Rj.cosu = cf.x; Rj.facty = cf.y;
+            Rj.cdxu = ld_div(tb.cdxu + (size_t)i * M + j);
+        }
+        const Divisor d4xt = ld_div(&tb.xt[i].d4xt);
+        const Taper taper = {a.two_rd, a.m2c0, a.s_max};
 
         // ---- this column: values, vertical differences and gradients ------------------------------
         const double Tc = ld(T, c), Sc = ld(S, c);
@@ -368,7 +423,14 @@ iso_pre_kernel(const PreArgs a) {
 
         // ---- top face: Ai_bx, Ai_by, K_33 (isoneutral.py:173-225) and flux_top (diffusion.py:85-111) --
         if (inT) {
-            const RowTab Rs = row[j - 1 - jlo];
+            struct { Divisor dyu; double cosu, facty; } Rs;
+            {
+                const RowTab* r = tb.row + j - 1;
+                Rs.dyu = ld_div(&r->dyu);
+                const double2 cf = __ldg(reinterpret_cast<const double2*>(&r->cosu));
+                Rs.cosu = cf.x; Rs.facty = cf.y;
+            }
+            const double r_cdxu_w = __ldg(&tb.cdxu[(size_t)(i - 1) * M + j].ry);
             const double Tw = ld(T, cw), Sw = ld(S, cw), Tpw = ld(T, cw + 1), Spw = ld(S, cw + 1);
             const double Ts = ld(T, cs), Ss = ld(S, cs), Tps = ld(T, cs + 1), Sps = ld(S, cs + 1);
             // raw differences [ip|jp][kr]: tr(i+ip,j,k+kr) - tr(i-1+ip,j,k+kr) and the same in y
@@ -377,7 +439,7 @@ iso_pre_kernel(const PreArgs a) {
             const double dTy[2][2] = {{Tc - Ts, Tp - Tps}, {dTyc, Tpn - Tp}};
             const double dSy[2][2] = {{Sc - Ss, Sp - Sps}, {dSyc, Spn - Sp}};
             // metric factors with the U/V masks folded in
-            const double mx[2][2] = {{sel(a.maskU[cw] != 0, Rj.r_cdxu_w), sel(a.maskU[cw + 1] != 0, Rj.r_cdxu_w)},
+            const double mx[2][2] = {{sel(a.maskU[cw] != 0, r_cdxu_w), sel(a.maskU[cw + 1] != 0, r_cdxu_w)},
                                      {mrdx, sel(a.maskU[c + 1] != 0, Rj.cdxu.ry)}};
             const double my[2][2] = {{sel(a.maskV[cs] != 0, Rs.dyu.ry), sel(a.maskV[cs + 1] != 0, Rs.dyu.ry)},
                                      {mrdy, sel(a.maskV[c + 1] != 0, Rj.dyu.ry)}};
@@ -386,13 +448,13 @@ iso_pre_kernel(const PreArgs a) {
                 drTu = __ldg(a.drdT + c + 1);
                 drSu = __ldg(a.drdS + c + 1);
             } else {
-                eos_drho<EOS>(Sp, Tp, lev[k + 1].pabs, drTu, drSu);
+                eos_drho<EOS>(Sp, Tp, __ldg(&tb.lev[k + 1].pabs), drTu, drSu);
                 const bool m = a.maskT[c + 1];
                 drTu = sel(m, drTu);
                 drSu = sel(m, drSu);
             }
             const double KcW = sel(mWc1, Kc);                                 // K_iso * maskW
-            const double cx[2] = {__ldg(a.g.dxu + i - 1) * KcW, __ldg(a.g.dxu + i) * KcW};
+            const double cx[2] = {__ldg(&tb.xt[i - 1].dxu) * KcW, __ldg(&tb.xt[i].dxu) * KcW};
             const double cy[2] = {Rs.facty * KcW, Rj.facty * KcW};
             double Ax[2][2], Ay[2][2];
             double sumx = 0.0, sumy = 0.0;
@@ -424,10 +486,10 @@ iso_pre_kernel(const PreArgs a) {
             store_pair(a.Ai_bx + c * 4 + 2, Ax[1][0], Ax[1][1]);
             store_pair(a.Ai_by + c * 4, Ay[0][0], Ay[0][1]);
             store_pair(a.Ai_by + c * 4 + 2, Ay[1][0], Ay[1][1]);
-            a.K_33[c] = fma(sumx, d4xt[0].ry, sumy * Rj.d4ytc.ry);
+            a.K_33[c] = fma(sumx, d4xt.ry, sumy * Rj.d4ytc.ry);
             if (FLUX) {
-                fl[0][2] = flux_top(Kc, Ax, Ay, dTx, dTy, Rs.cosu, Rj.cosu, Rj.cost, d4xt[0], Rj.d4ytc);
-                fl[1][2] = flux_top(Kc, Ax, Ay, dSx, dSy, Rs.cosu, Rj.cosu, Rj.cost, d4xt[0], Rj.d4ytc);
+                fl[0][2] = flux_top(Kc, Ax, Ay, dTx, dTy, Rs.cosu, Rj.cosu, Rj.cost, d4xt, Rj.d4ytc);
+                fl[1][2] = flux_top(Kc, Ax, Ay, dSx, dSy, Rs.cosu, Rj.cosu, Rj.cost, d4xt, Rj.d4ytc);
             }
         }
     }
@@ -439,23 +501,27 @@ iso_pre_kernel(const PreArgs a) {
     }
 }
 
-size_t pre_smem_bytes(int nz) {
-    const int jr = kPreBlock / nz + 3;
-    return 64 * 8 + (size_t)nz * sizeof(LevTab) + (size_t)jr * sizeof(RowTab) + sizeof(Divisor);
-}
+size_t pre_tables_doubles(int N, int M, int nz) { return tables_doubles(N, M, nz); }
 
 template <int EOS>
-static void launch_pre_eos(cudaStream_t s, const PreArgs& a, dim3 grid, size_t smem) {
+static void launch_pre_eos(cudaStream_t s, const PreArgs& a, dim3 grid) {
     if (a.with_flux)
-        iso_pre_kernel<EOS, true><<<grid, kPreBlock, smem, s>>>(a);
+        iso_pre_kernel<EOS, true><<<grid, kPreBlock, 0, s>>>(a);
     else
-        iso_pre_kernel<EOS, false><<<grid, kPreBlock, smem, s>>>(a);
+        iso_pre_kernel<EOS, false><<<grid, kPreBlock, 0, s>>>(a);
 }
 
-void launch_iso_pre(cudaStream_t s, const PreArgs& a) {
+void launch_iso_pre(cudaStream_t s, const PreArgs& a0) {
+    PreArgs a = a0;
     const int N = a.g.N, M = a.g.M, nz = a.g.nz;
     const size_t ncell = (size_t)N * M * nz;
     if (ncell == 0) return;
+    a.two_rd = 2.0 / a.iso_dslope;
+    a.m2c0 = -2.0 * a.iso_slopec / a.iso_dslope;
+    a.s_max = (345.0 + a.iso_slopec / a.iso_dslope) * a.iso_dslope;
+    setup_kernel<<<min(64, (N * M + 255) / 256), 256, 0, s>>>(a.g, a.tables);
+    count_launch();
+    if (!check_launch("setup_kernel")) return;
     if (a.eos == 5) {
         eos5_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, s>>>(ncell, nz, a.temp, a.salt, a.tau, a.maskT, a.g.zt,
                                                                    a.drdT, a.drdS);
@@ -463,13 +529,12 @@ void launch_iso_pre(cudaStream_t s, const PreArgs& a) {
         if (!check_launch("eos5_kernel")) return;
     }
     dim3 grid((M * nz + kPreBlock - 1) / kPreBlock, N);
-    const size_t smem = pre_smem_bytes(nz);
     switch (a.eos) {
-    case 1: launch_pre_eos<1>(s, a, grid, smem); break;
-    case 2: launch_pre_eos<2>(s, a, grid, smem); break;
-    case 3: launch_pre_eos<3>(s, a, grid, smem); break;
-    case 4: launch_pre_eos<4>(s, a, grid, smem); break;
-    default: launch_pre_eos<5>(s, a, grid, smem); break;
+    case 1: launch_pre_eos<1>(s, a, grid); break;
+    case 2: launch_pre_eos<2>(s, a, grid); break;
+    case 3: launch_pre_eos<3>(s, a, grid); break;
+    case 4: launch_pre_eos<4>(s, a, grid); break;
+    default: launch_pre_eos<5>(s, a, grid); break;
     }
     count_launch();
     check_launch("iso_pre_kernel");
