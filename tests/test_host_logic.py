@@ -1,0 +1,111 @@
+"""Host-side logic that needs no GPU: state validation, synthetic generators, error behaviour of the
+reference-facing functions, slab decomposition arithmetic."""
+import numpy as np
+import pytest
+
+from helpers import copy_state
+
+torch = pytest.importorskip("torch")
+
+
+def small_state(**kw):
+    from veros_b200 import synthetic
+
+    return synthetic.random_state(6, 5, 4, **kw)
+
+
+def test_state_from_numpy_and_validation():
+    from veros_b200.state import IsoState
+
+    st = small_state()
+    s = IsoState.from_numpy(st, "cpu")
+    assert s.settings.nx == 6 and s.settings.nz == 4
+    assert s.variables.maskT.dtype == torch.uint8 and s.variables.kbot.dtype == torch.int32
+    assert tuple(s.variables.temp.shape) == (10, 9, 4, 3)
+    back = s.to_numpy(["temp", "Ai_ez"])
+    assert np.array_equal(back["temp"], st["temp"])
+    s.variables.K_11 = s.variables.K_11[:, :, :3]
+    with pytest.raises(ValueError, match="K_11"):
+        s.validate()
+    s = IsoState.from_numpy(st, "cpu")
+    s.variables.salt = s.variables.salt.float()
+    with pytest.raises(TypeError, match="salt"):
+        s.validate()
+    bad = copy_state(st)
+    bad["eq_of_state_type"] = 9
+    with pytest.raises(ValueError, match="equation of state"):
+        IsoState.from_numpy(bad, "cpu")
+    bad = copy_state(st)
+    del bad["int_drhodT"]
+    with pytest.raises(ValueError, match="int_drhodT"):
+        IsoState.from_numpy(bad, "cpu")
+    bad["enable_conserve_energy"] = False
+    IsoState.from_numpy(bad, "cpu")  # fine without the energy fields
+
+
+def test_kernel_output_matches_reference_factory():
+    from veros_b200.state import KernelOutput, Variables
+
+    out = KernelOutput(K_11=1, K_22=2)
+    assert out._fields == ("K_11", "K_22") and out.K_22 == 2
+    vs = Variables()
+    vs.update(out)
+    assert vs.K_11 == 1
+
+
+def test_ops_refuse_cpu_tensors():
+    from veros_b200 import utilities
+
+    x = torch.zeros((2, 3, 5), dtype=torch.float64)
+    m = torch.zeros((2, 3, 5), dtype=torch.bool)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        utilities.solve_tridiagonal(x, x, x, x, m, m)
+    with pytest.raises(ValueError, match="identical shape"):
+        utilities.solve_implicit(x, x[:1], x, x, m, m)
+    with pytest.raises(TypeError):
+        utilities.solve_implicit(*(x.float(),) * 4, m, m)
+
+
+def test_masks_follow_calc_topo_rules():
+    from veros_b200 import synthetic
+
+    st = synthetic.random_state(9, 8, 6, enable_cyclic_x=True)
+    kbot, T, U, V, W = (st[k] for k in ("kbot", "maskT", "maskU", "maskV", "maskW"))
+    k = np.arange(6)[None, None, :]
+    assert np.array_equal(T[2:-2], ((kbot > 0)[..., None] & (kbot[..., None] - 1 <= k))[2:-2])
+    assert np.array_equal(U[:-1][2:-2], (T[:-1] & T[1:])[2:-2])
+    assert np.array_equal(V[:, :-1], T[:, :-1] & T[:, 1:])
+    assert np.array_equal(W[:, :, :-1], T[:, :, :-1] & T[:, :, 1:])
+    assert np.array_equal(T[-2:], T[2:4]) and np.array_equal(T[:2], T[-4:-2])  # cyclic ghost columns
+
+
+def test_analytic_slabs_tile_the_global_state():
+    from veros_b200 import decomp, synthetic
+
+    full = synthetic.make_workload("global_4deg")
+    nxg = full["nx"]
+    for world in (2, 3):
+        for rank in range(world):
+            x0, x1 = decomp.slab_bounds(nxg, world, rank)
+            part = synthetic.make_workload("global_4deg", nx=x1 - x0, x_offset=x0, nx_global=nxg)
+            for k in ("temp", "salt", "K_iso", "kbot", "maskT", "int_drhodT"):
+                assert np.array_equal(part[k], full[k][x0:x1 + 4]), (k, world, rank)
+    with pytest.raises(ValueError):
+        decomp.slab_bounds(90, 4, 0)
+    assert decomp.neighbours(0, 4, True) == (3, 1) and decomp.neighbours(0, 4, False) == (None, 1)
+    assert decomp.neighbours(3, 4, True) == (2, 0) and decomp.neighbours(3, 4, False) == (2, None)
+
+
+def test_oracle_slab_invariance():
+    """The property the multi-GPU design rests on: a slab computed with its 2-cell
+    halos reproduces the global interior bit for bit -- checked here with the CPU oracle."""
+    from oracle import oracle
+    from veros_b200 import synthetic
+
+    full = synthetic.make_workload("global_4deg", nx=24, ny=16)
+    ref = oracle.isoneutral_step(copy_state(full))
+    for x0, x1 in ((0, 12), (12, 24)):
+        part = synthetic.make_workload("global_4deg", nx=x1 - x0, ny=16, x_offset=x0, nx_global=24)
+        got = oracle.isoneutral_step(part)
+        for k in ("temp", "salt", "dtemp_iso", "dsalt_iso", "P_diss_iso", "K_33", "Ai_ez", "Ai_by"):
+            assert np.array_equal(got[k][2:-2], ref[k][x0 + 2:x1 + 2]), k

@@ -1,0 +1,252 @@
+"""JAX / XLA side of the drop-in: registers the entry points of libveros_b200.so as XLA GPU custom-call
+targets and rebinds Veros's isoneutral functions to them.
+
+    import veros_b200.jax_glue as glue
+    glue.install()          # after `import veros.core`, backend == "jax", device == "gpu"
+
+NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no jax/jaxlib, so this
+module is written against the reference's own use of the same JAX APIs (veros/core/special/tdma_.py:
+PyCapsule "xla._CUSTOM_CALL_TARGET" :25-27 of tdma_cuda_.pyx, jax.ffi.register_ffi_target(...,
+platform="CUDA", api_version=0) :34-37, jax._src.interpreters.mlir.custom_call :173-180, Primitive /
+def_abstract_eval / register_lowering :184-193; reference pin jax==0.11.0).  The tests exercise the
+same C symbols through ctypes instead (veros_b200/_lib.py); INTEGRATION.md shows the wiring.
+
+Nothing here falls back to jnp: if the library or a GPU is missing, install() raises.
+"""
+import ctypes
+
+from . import _lib
+
+_CAPSULE_NAME = b"xla._CUSTOM_CALL_TARGET"
+_registered = False
+
+# XLA target name -> C symbol
+TARGETS = {
+    "veros_b200_solve_implicit_f64": "veros_b200_solve_implicit_f64",
+    "veros_b200_iso_pre_f64": "veros_b200_iso_pre_f64",
+    "veros_b200_iso_diffusion_f64": "veros_b200_iso_diffusion_f64",
+    "veros_b200_iso_step_f64": "veros_b200_iso_step_f64",
+    # the reference's own target names, served by the z-major compatible kernels (shim below)
+    "tdma_cuda_double": "veros_b200_tdma_zmajor_f64",
+    "tdma_cuda_float": "veros_b200_tdma_zmajor_f32",
+}
+
+
+def capsule(symbol):
+    """PyCapsule around a C entry point, named as XLA expects (tdma_cuda_.pyx:23-27)."""
+    fn = getattr(_lib.lib(), symbol)
+    addr = ctypes.cast(fn, ctypes.c_void_p).value
+    new = ctypes.pythonapi.PyCapsule_New
+    new.restype = ctypes.py_object
+    new.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
+    return new(addr, _CAPSULE_NAME, None)
+
+
+# ---- drop-in for veros.core.special.tdma_cuda_ (tdma_cuda_.pyx:18-30) ------------------------------
+def build_tridiag_descriptor(num_systems, system_depth):
+    return bytes(_lib.TridiagDescriptor(num_systems=int(num_systems), system_depth=int(system_depth)))
+
+
+def gpu_custom_call_targets():
+    return {name: capsule(TARGETS[name]) for name in ("tdma_cuda_double", "tdma_cuda_float")}
+
+
+def install_tdma_shim():
+    """Make the UNMODIFIED reference `veros.core.special.tdma_` use this library's TDMA: it imports
+    `veros.core.special.tdma_cuda_` and reads `gpu_custom_call_targets` / `build_tridiag_descriptor`
+    from it (tdma_.py:9-14,34-37,165).  Must run before `veros.core.special.tdma_` is imported."""
+    import sys
+    import types
+
+    mod = types.ModuleType("veros.core.special.tdma_cuda_")
+    mod.gpu_custom_call_targets = gpu_custom_call_targets()
+    mod.build_tridiag_descriptor = build_tridiag_descriptor
+    sys.modules["veros.core.special.tdma_cuda_"] = mod
+    return mod
+
+
+# ---- XLA registration -----------------------------------------------------------------------------
+def register():
+    global _registered
+    if _registered:
+        return
+    import jax
+
+    for name, symbol in TARGETS.items():
+        if name.startswith("tdma_cuda_"):
+            continue  # registered by the reference's tdma_.py through the shim
+        jax.ffi.register_ffi_target(name, capsule(symbol), platform="CUDA", api_version=0)
+    _registered = True
+
+
+def _custom_call(name, operands, result_avals, descriptor, aliases):
+    """Emit one custom call with native row-major layouts and in-place state (operand_output_aliases)."""
+    import jaxlib.mlir.ir as ir
+    from jax._src.interpreters.mlir import custom_call
+    from jax.interpreters import mlir
+
+    result_types = [ir.RankedTensorType.get(a.shape, mlir.dtype_to_ir_type(a.dtype)) for a in result_avals]
+    return custom_call(
+        name.encode(), operands=operands, result_types=result_types, backend_config=bytes(descriptor),
+        operand_output_aliases=aliases,
+    ).results
+
+
+def _make_primitive(name, n_inout, inout_first, has_workspace, workspace_bytes, fresh_like=()):
+    """Primitive whose first/last `n_inout` operands are returned updated (aliased), followed by fresh
+    results shaped like the operands listed in `fresh_like`, followed by the scratch buffer."""
+    import numpy as np
+    from jax.core import ShapedArray
+    from jax.extend.core import Primitive
+    from jax.interpreters import mlir, xla
+
+    prim = Primitive(name)
+    prim.multiple_results = True
+
+    def abstract_eval(*avals, descriptor):
+        n = len(avals)
+        idx = range(n_inout) if inout_first else range(n - n_inout, n)
+        outs = [ShapedArray(avals[i].shape, avals[i].dtype) for i in idx]
+        outs += [ShapedArray(avals[i].shape, avals[i].dtype) for i in fresh_like]
+        if has_workspace:
+            outs.append(ShapedArray((max(1, workspace_bytes(descriptor) // 8),), np.float64))
+        return outs
+
+    def lowering(ctx, *operands, descriptor):
+        n = len(operands)
+        idx = list(range(n_inout)) if inout_first else list(range(n - n_inout, n))
+        aliases = {op: res for res, op in enumerate(idx)}
+        return _custom_call(name, operands, ctx.avals_out, descriptor, aliases)
+
+    prim.def_impl(lambda *a, **k: xla.apply_primitive(prim, *a, **k))
+    prim.def_abstract_eval(abstract_eval)
+    mlir.register_lowering(prim, lowering, platform="cuda")
+    return prim
+
+
+_prims = {}
+
+
+def _primitives():
+    if _prims:
+        return _prims
+    L = _lib.lib()
+
+    def ws(fn):
+        return lambda d: int(getattr(L, fn)(bytes(d), len(bytes(d))))
+
+    _prims["pre"] = _make_primitive("veros_b200_iso_pre_f64", 7, False, True, ws("veros_b200_iso_pre_workspace_bytes"))
+    _prims["diffusion"] = _make_primitive("veros_b200_iso_diffusion_f64", 3, True, True,
+                                          ws("veros_b200_iso_diffusion_workspace_bytes"))
+    _prims["step"] = _make_primitive("veros_b200_iso_step_f64", 12, True, True, ws("veros_b200_iso_step_workspace_bytes"))
+    _prims["solve"] = _make_primitive("veros_b200_solve_implicit_f64", 0, True, False, None, fresh_like=(0,))
+    return _prims
+
+
+def _iso_descriptor(state, flags=0):
+    st, vs = state.settings, state.variables
+    N, M, nz = vs.K_iso.shape
+    return _lib.IsoDescriptor(
+        nx_tot=N, ny_tot=M, nz=nz, eq_of_state_type=st.eq_of_state_type,
+        enable_conserve_energy=int(st.enable_conserve_energy), flags=flags, K_iso_steep=st.K_iso_steep,
+        iso_slopec=st.iso_slopec, iso_dslope=st.iso_dslope, dt_tracer=st.dt_tracer, grav=st.grav, rho_0=st.rho_0)
+
+
+_METRICS = ("dxt", "dxu", "dyt", "dyu", "cost", "cosu", "dzt", "dzw")
+_PRE_OUT = ("Ai_ez", "Ai_nz", "Ai_bx", "Ai_by", "K_11", "K_22", "K_33")
+
+
+def _i32(x):
+    import jax.numpy as jnp
+
+    return jnp.asarray(x, dtype=jnp.int32).reshape((1,))
+
+
+def _u8(x):
+    import jax.numpy as jnp
+
+    return x.astype(jnp.uint8)
+
+
+def make_replacements():
+    """Builds @veros_kernel / @veros_routine objects with the reference's signatures
+    (isoneutral.py:18, diffusion.py:286-295, utilities.py:51-59)."""
+    import jax.numpy as jnp
+    from veros import KernelOutput, veros_kernel, veros_routine
+
+    P = _primitives()
+
+    @veros_kernel
+    def isoneutral_diffusion_pre(state):
+        vs = state.variables
+        ops = [vs.temp, vs.salt, _i32(vs.tau), vs.K_iso, _u8(vs.maskT), _u8(vs.maskU), _u8(vs.maskV), _u8(vs.maskW)]
+        ops += [getattr(vs, n) for n in _METRICS] + [vs.zt] + [getattr(vs, n) for n in _PRE_OUT]
+        out = P["pre"].bind(*ops, descriptor=bytes(_iso_descriptor(state)))  # bytes: hashable jit-static param
+        return KernelOutput(**dict(zip(_PRE_OUT, out[:7])))
+
+    @veros_kernel(static_args=("istemp", "skew"))
+    def _diffusion_kernel(state, tr, istemp, skew):
+        vs, st = state.variables, state.settings
+        energy = st.enable_conserve_energy
+        dtr = vs.dtemp_iso if istemp else vs.dsalt_iso
+        dummy = jnp.zeros((1,), dtype=tr.dtype)
+        Pd = (vs.P_diss_skew if skew else vs.P_diss_iso) if energy else dummy
+        X = (vs.int_drhodT if istemp else vs.int_drhodS) if energy else dummy
+        K = vs.K_gm if skew else vs.K_iso
+        ops = [tr, dtr, Pd, _i32(vs.tau), _i32(vs.taup1), K] + [getattr(vs, n) for n in _PRE_OUT]
+        ops += [_u8(vs.maskT), _u8(vs.maskW), vs.kbot.astype(jnp.int32)] + [getattr(vs, n) for n in _METRICS] + [X]
+        tr_new, dtr_new, P_new, _ = P["diffusion"].bind(
+            *ops, descriptor=bytes(_iso_descriptor(state, _lib.FLAG_SKEW if skew else 0)))
+        out = {("temp" if istemp else "salt"): tr_new, ("dtemp_iso" if istemp else "dsalt_iso"): dtr_new}
+        if energy:
+            out["P_diss_skew" if skew else "P_diss_iso"] = P_new
+        return KernelOutput(**out)
+
+    @veros_routine
+    def isoneutral_diffusion(state, tr, istemp):
+        state.variables.update(_diffusion_kernel(state, tr, istemp, False))
+
+    @veros_routine
+    def isoneutral_skew_diffusion(state, tr, istemp):
+        state.variables.update(_diffusion_kernel(state, tr, istemp, True))
+
+    @veros_kernel
+    def solve_implicit(a, b, c, d, water_mask, edge_mask, b_edge=None, d_edge=None):
+        if not a.shape == b.shape == c.shape == d.shape:
+            raise ValueError("all inputs must have identical shape")
+        if not a.dtype == b.dtype == c.dtype == d.dtype:
+            raise ValueError("all inputs must have the same dtype")
+        nz = a.shape[-1]
+        flags = (_lib.HAS_B_EDGE if b_edge is not None else 0) | (_lib.HAS_D_EDGE if d_edge is not None else 0)
+        desc = _lib.SolveDescriptor(num_systems=a.size // nz, system_depth=nz, flags=flags, reserved=0)
+        ops = [a, b, c, d, _u8(water_mask), _u8(edge_mask), b if b_edge is None else b_edge, d if d_edge is None else d_edge]
+        return P["solve"].bind(*ops, descriptor=bytes(desc))[0]
+
+    def solve_tridiagonal(a, b, c, d, water_mask, edge_mask):
+        return solve_implicit(a, b, c, d, water_mask, edge_mask)
+
+    return dict(isoneutral_diffusion_pre=isoneutral_diffusion_pre, isoneutral_diffusion=isoneutral_diffusion,
+                isoneutral_skew_diffusion=isoneutral_skew_diffusion, solve_implicit=solve_implicit,
+                solve_tridiagonal=solve_tridiagonal)
+
+
+def install():
+    """Idempotent; re-apply after anything reloads veros.core (test/pyom_consistency/conftest.py:21-32)."""
+    from veros import runtime_settings as rs
+
+    if rs.backend != "jax" or rs.device != "gpu":
+        raise RuntimeError("veros_b200 has no CPU path: it needs backend='jax' and device='gpu'")
+    _lib.lib()
+    register()
+    import veros.core.isoneutral as iso_pkg
+    import veros.core.operators as operators
+    import veros.core.utilities as utilities
+
+    r = make_replacements()
+    iso_pkg.isoneutral_diffusion_pre = r["isoneutral_diffusion_pre"]
+    iso_pkg.isoneutral_diffusion = r["isoneutral_diffusion"]
+    iso_pkg.isoneutral_skew_diffusion = r["isoneutral_skew_diffusion"]
+    utilities.solve_implicit = r["solve_implicit"]
+    utilities.solve_tridiagonal = r["solve_tridiagonal"]
+    operators.solve_tridiagonal = r["solve_tridiagonal"]
+    return r
