@@ -72,14 +72,15 @@ def test_workspace_sizes(lib):
     from veros_b200 import _lib
 
     d = _lib.IsoDescriptor(nx_tot=20, ny_tot=10, nz=7, eq_of_state_type=1, iso_dslope=1e-3, iso_slopec=1e-3, dt_tracer=1.0)
-    n3 = 20 * 10 * 7
+    n3 = 20 * 10 * 7  # even, so no alignment padding in the sizes below
     o = bytes(d)
     pre1 = lib.veros_b200_iso_pre_workspace_bytes(o, len(o))
     d.eq_of_state_type = 5
     o5 = bytes(d)
     pre5 = lib.veros_b200_iso_pre_workspace_bytes(o5, len(o5))
     assert pre1 > 0 and pre5 - pre1 == 2 * 8 * n3  # drdT, drdS scratch for TEOS-10
-    assert lib.veros_b200_iso_diffusion_workspace_bytes(o, len(o)) == 4 * 8 * n3
+    # fluxes (3) + dissipation (1) per tracer, metric tables
+    assert lib.veros_b200_iso_diffusion_workspace_bytes(o, len(o)) == 4 * 8 * n3 + pre1
     assert lib.veros_b200_iso_step_workspace_bytes(o5, len(o5)) == 8 * 8 * n3 + pre5
     assert lib.veros_b200_iso_step_workspace_bytes(b"x", 1) == 0
     lib.veros_b200_clear_error()

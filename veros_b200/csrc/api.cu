@@ -7,6 +7,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tables.cuh"
 
 namespace vb {
 
@@ -82,10 +83,13 @@ static Grid make_grid(const VerosB200IsoDescriptor* d, void* dxt, void* dxu, voi
     return g;
 }
 
-static size_t pre_ws_doubles(const VerosB200IsoDescriptor* d) {
-    const size_t tabs = (pre_tables_doubles(d->nx_tot, d->ny_tot, d->nz) + 1) & ~(size_t)1;  // keep 16 B alignment
-    return tabs + (d->eq_of_state_type == 5 ? (size_t)2 * d->nx_tot * d->ny_tot * d->nz : 0);
+static size_t tabs_doubles(const VerosB200IsoDescriptor* d) {
+    return (tables_doubles(d->nx_tot, d->ny_tot, d->nz) + 1) & ~(size_t)1;  // keep 16 B alignment behind it
 }
+static size_t drd_doubles(const VerosB200IsoDescriptor* d) {
+    return d->eq_of_state_type == 5 ? (size_t)2 * d->nx_tot * d->ny_tot * d->nz : 0;
+}
+static size_t pre_ws_doubles(const VerosB200IsoDescriptor* d) { return tabs_doubles(d) + drd_doubles(d); }
 
 }  // namespace vb
 
@@ -142,7 +146,9 @@ void veros_b200_iso_pre_f64(void* stream, void** B, const char* opaque, size_t l
     a.K_22 = (double*)B[29];
     a.K_33 = (double*)B[30];
     a.tables = (double*)B[31];
-    a.drdT = a.tables + ((pre_tables_doubles(d->nx_tot, d->ny_tot, d->nz) + 1) & ~(size_t)1);
+    a.tables_ready = 0;
+    a.dt_tracer = d->dt_tracer;
+    a.drdT = a.tables + tabs_doubles(d);
     a.drdS = a.drdT + n3;
     a.with_flux = 0;
     for (int t = 0; t < 2; ++t)
@@ -190,7 +196,11 @@ void veros_b200_iso_diffusion_f64(void* stream, void** B, const char* opaque, si
     a.dt_tracer = d->dt_tracer;
     a.grav = d->grav;
     a.rho_0 = d->rho_0;
-    launch_iso_diffusion_ws(s, a, (double*)B[28]);
+    double* ws = (double*)B[28];
+    a.tables = ws + diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 1);
+    launch_setup_tables(s, a.g, d->dt_tracer, a.tables);
+    if (veros_b200_last_error()) return;
+    launch_iso_diffusion_ws(s, a, ws);
 }
 
 void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t len) {
@@ -221,9 +231,13 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     p.K_11 = (double*)B[40];
     p.K_22 = (double*)B[41];
     p.K_33 = (double*)B[42];
-    p.tables = ws + 8 * n3;  // behind the six flux and two dissipation arrays
-    p.drdT = p.tables + ((pre_tables_doubles(d->nx_tot, d->ny_tot, d->nz) + 1) & ~(size_t)1);
+    p.tables = ws + diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 2);  // behind the flux/scratch arrays
+    p.tables_ready = 1;
+    p.dt_tracer = d->dt_tracer;
+    p.drdT = p.tables + tabs_doubles(d);
     p.drdS = p.drdT + n3;
+    launch_setup_tables(s, p.g, d->dt_tracer, p.tables);
+    if (veros_b200_last_error()) return;
     p.with_flux = 1;
     for (int t = 0; t < 2; ++t)
         for (int q = 0; q < 3; ++q) p.flux[t][q] = ws + (size_t)(3 * t + q) * n3;
@@ -260,6 +274,7 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     a.skew = 0;
     a.energy = energy ? 1 : 0;
     a.fluxes_ready = 1;
+    a.tables = p.tables;
     a.dt_tracer = d->dt_tracer;
     a.grav = d->grav;
     a.rho_0 = d->rho_0;
@@ -273,7 +288,7 @@ size_t veros_b200_iso_pre_workspace_bytes(const char* opaque, size_t len) {
 
 size_t veros_b200_iso_diffusion_workspace_bytes(const char* opaque, size_t len) {
     const auto* d = unpack<VerosB200IsoDescriptor>(opaque, len, "iso_diffusion_workspace_bytes: bad descriptor");
-    return d ? 8 * diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 1) : 0;
+    return d ? 8 * (diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 1) + tabs_doubles(d)) : 0;
 }
 
 size_t veros_b200_iso_step_workspace_bytes(const char* opaque, size_t len) {

@@ -30,6 +30,8 @@ struct PreArgs {
     double *Ai_ez, *Ai_nz, *Ai_bx, *Ai_by, *K_11, *K_22, *K_33;
     double *drdT, *drdS;  // workspace, EOS 5 only
     double* tables;       // workspace, pre_tables_doubles() doubles: metric tables built per call
+    int tables_ready;     // the caller already ran launch_setup_tables on `tables`
+    double dt_tracer;
     double two_rd, m2c0, s_max;  // taper constants (filled by launch_iso_pre)
     double* flux[2][3];   // [temp|salt][east|north|top] outputs when with_flux
     int with_flux;
@@ -55,12 +57,12 @@ struct DiffArgs {
     const int32_t* kbot;
     int skew, energy;
     int fluxes_ready;  // the fused slope+flux kernel already filled the flux workspace
+    double* tables;    // metric tables (tables.cuh), built by launch_setup_tables
     double dt_tracer, grav, rho_0;
 };
 
 // ---- launchers (one per translation unit) -----------------------------------------------------
 void launch_iso_pre(cudaStream_t s, const PreArgs& a);
-size_t pre_tables_doubles(int N, int M, int nz);
 size_t diffusion_workspace_doubles(int N, int M, int nz, int ntr);
 void launch_iso_diffusion_ws(cudaStream_t s, const DiffArgs& a, double* workspace);
 void launch_solve_implicit(cudaStream_t s, int ncol, int nz, const double* a, const double* b, const double* c,

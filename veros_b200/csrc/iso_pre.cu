@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "eos.cuh"
 #include "flux_device.cuh"
+#include "tables.cuh"
 
 namespace vb {
 
@@ -123,52 +124,8 @@ eos5_kernel(size_t ncell, int nz, const double* __restrict__ temp, const double*
     drdS[c] = dS;
 }
 
-// Metric tables, built once per call by setup_kernel in the workspace (a few KB, L1/L2 resident):
-//   LevTab[nz]   4 dzt[k] (+ correctly rounded reciprocal), 1/dzw[k], dzw[k], |zt[k]|
-//   RowTab[M]    dyu, cost, (4 dyt) cost (+ reciprocals), cosu, cosu*dyu
-//   XTab[N]      4 dxt[i] (+ reciprocal), dxu[i]
-//   Cdxu[N][M]   cost[j]*dxu[i] (+ reciprocal)
-// No per-thread division by a grid metric remains in the main kernel.
-struct RowTab {
-    Divisor dyu, cost, d4ytc;
-    double cosu, facty;
-};
-struct LevTab {
-    Divisor d4zt;
-    double rdzw, dzw, pabs, pad;
-};
-struct XTab {
-    Divisor d4xt;
-    double dxu, pad;
-};
-struct Tables {
-    const LevTab* lev;
-    const RowTab* row;
-    const XTab* xt;
-    const Divisor* cdxu;
-};
-
-__host__ __device__ inline size_t tables_doubles(int N, int M, int nz) {
-    return (size_t)nz * (sizeof(LevTab) / 8) + (size_t)M * (sizeof(RowTab) / 8) + (size_t)N * (sizeof(XTab) / 8) +
-           (size_t)N * M * (sizeof(Divisor) / 8);
-}
-
-__host__ __device__ inline Tables tables_at(double* base, int N, int M, int nz) {
-    Tables t;
-    LevTab* lev = reinterpret_cast<LevTab*>(base);
-    RowTab* row = reinterpret_cast<RowTab*>(lev + nz);
-    XTab* xt = reinterpret_cast<XTab*>(row + M);
-    Divisor* cd = reinterpret_cast<Divisor*>(xt + N);
-    (void)N;
-    t.lev = lev;
-    t.row = row;
-    t.xt = xt;
-    t.cdxu = cd;
-    return t;
-}
-
 __global__ void __launch_bounds__(256)
-setup_kernel(const Grid g, double* base) {
+setup_kernel(const Grid g, const double dt, double* base) {
     const int N = g.N, M = g.M, nz = g.nz;
     const Tables t = tables_at(base, N, M, nz);
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,10 +133,10 @@ setup_kernel(const Grid g, double* base) {
     for (int k = tid; k < nz; k += nth) {
         LevTab e;
         e.d4zt = make_divisor(4.0 * g.dzt[k]);
-        e.dzw = g.dzw[k];
-        e.rdzw = 1.0 / e.dzw;
-        e.pabs = fabs(g.zt[k]);
-        e.pad = 0.0;
+        e.dzt = make_divisor(g.dzt[k]);
+        e.dzw = make_divisor(g.dzw[k]);
+        e.dt_dzw = __ddiv_rn(dt, g.dzw[k]);
+        e.pabs = g.zt ? fabs(g.zt[k]) : 0.0;
         const_cast<LevTab*>(t.lev)[k] = e;
     }
     for (int j = tid; j < M; j += nth) {
@@ -188,6 +145,7 @@ setup_kernel(const Grid g, double* base) {
         e.dyu = make_divisor(dyu);
         e.cost = make_divisor(cost);
         e.d4ytc = make_divisor(4.0 * g.dyt[j] * cost);
+        e.cdyt = make_divisor(cost * g.dyt[j]);
         e.cosu = cosu;
         e.facty = cosu * dyu;
         const_cast<RowTab*>(t.row)[j] = e;
@@ -201,13 +159,17 @@ setup_kernel(const Grid g, double* base) {
     }
     for (int q = tid; q < N * M; q += nth) {
         const int i = q / M, j = q - i * M;
-        const_cast<Divisor*>(t.cdxu)[q] = make_divisor(g.cost[j] * g.dxu[i]);
+        CellTab e;
+        e.cdxu = make_divisor(g.cost[j] * g.dxu[i]);
+        e.cdxt = make_divisor(g.cost[j] * g.dxt[i]);
+        const_cast<CellTab*>(t.cell)[q] = e;
     }
 }
 
-__device__ __forceinline__ Divisor ld_div(const Divisor* p) {
-    const double2 v = __ldg(reinterpret_cast<const double2*>(p));
-    return Divisor{v.x, v.y};
+void launch_setup_tables(cudaStream_t s, const Grid& g, double dt_tracer, double* tables) {
+    setup_kernel<<<min(148, (g.N * g.M + 255) / 256), 256, 0, s>>>(g, dt_tracer, tables);
+    count_launch();
+    check_launch("setup_kernel");
 }
 
 constexpr int kPreBlock = 128;
@@ -241,16 +203,23 @@ iso_pre_kernel(const PreArgs a) {
         const bool hasKm = k >= 1, hasKp = k < nz - 1;
         const int km = hasKm ? -1 : 0, kp = hasKp ? 1 : 0;  // clamped neighbours (pad_z_edges)
         const size_t ce = c + plane, cn = c + nz, cw = c - plane, cs = c - nz;
+        // Pull the neighbour planes / rows towards L1 now: their loads are scheduled late (register
+        // pressure) and would otherwise expose a DRAM round trip per face with only 12 resident warps.
+        {
+            auto pf = [](const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); };
+            pf(T + ce * 3); pf(S + ce * 3); pf(T + cn * 3); pf(S + cn * 3);
+            pf(a.K_iso + ce); pf(a.K_iso + cn);
+            if (inT) { pf(T + cw * 3); pf(S + cw * 3); pf(T + cs * 3); pf(S + cs * 3); }
+        }
         // metric table entries of this level / row / plane (read-only path, L1 resident)
         struct { Divisor d4zt; double rdzw, dzw, pabs; } L1, L0;
         {
             const LevTab* l1 = tb.lev + k;
             const LevTab* l0 = tb.lev + k + km;
             L1.d4zt = ld_div(&l1->d4zt);
-            const double2 a1 = __ldg(reinterpret_cast<const double2*>(&l1->rdzw));
-            L1.rdzw = a1.x; L1.dzw = a1.y; L1.pabs = __ldg(&l1->pabs);
-            const double2 a0 = __ldg(reinterpret_cast<const double2*>(&l0->rdzw));
-            L0.rdzw = a0.x; L0.dzw = a0.y; L0.pabs = 0.0; L0.d4zt = L1.d4zt;
+            const Divisor z1 = ld_div(&l1->dzw), z0 = ld_div(&l0->dzw);
+            L1.rdzw = z1.ry; L1.dzw = z1.y; L1.pabs = __ldg(&l1->pabs);
+            L0.rdzw = z0.ry; L0.dzw = z0.y; L0.pabs = 0.0; L0.d4zt = L1.d4zt;
         }
         struct { Divisor cdxu, dyu, cost, d4ytc; double cosu, facty; } Rj;
         {
@@ -260,7 +229,7 @@ iso_pre_kernel(const PreArgs a) {
             Rj.d4ytc = ld_div(&r->d4ytc);
             const double2 cf = __ldg(reinterpret_cast<const double2*>(&r->cosu));
             Rj.cosu = cf.x; Rj.facty = cf.y;
-            Rj.cdxu = ld_div(tb.cdxu + (size_t)i * M + j);
+            Rj.cdxu = ld_div(&tb.cell[(size_t)i * M + j].cdxu);
         }
         const Divisor d4xt = ld_div(&tb.xt[i].d4xt);
         const Taper taper = {a.two_rd, a.m2c0, a.s_max};
@@ -430,7 +399,7 @@ iso_pre_kernel(const PreArgs a) {
                 const double2 cf = __ldg(reinterpret_cast<const double2*>(&r->cosu));
                 Rs.cosu = cf.x; Rs.facty = cf.y;
             }
-            const double r_cdxu_w = __ldg(&tb.cdxu[(size_t)(i - 1) * M + j].ry);
+            const double r_cdxu_w = __ldg(&tb.cell[(size_t)(i - 1) * M + j].cdxu.ry);
             const double Tw = ld(T, cw), Sw = ld(S, cw), Tpw = ld(T, cw + 1), Spw = ld(S, cw + 1);
             const double Ts = ld(T, cs), Ss = ld(S, cs), Tps = ld(T, cs + 1), Sps = ld(S, cs + 1);
             // raw differences [ip|jp][kr]: tr(i+ip,j,k+kr) - tr(i-1+ip,j,k+kr) and the same in y
@@ -501,8 +470,6 @@ iso_pre_kernel(const PreArgs a) {
     }
 }
 
-size_t pre_tables_doubles(int N, int M, int nz) { return tables_doubles(N, M, nz); }
-
 template <int EOS>
 static void launch_pre_eos(cudaStream_t s, const PreArgs& a, dim3 grid) {
     if (a.with_flux)
@@ -519,9 +486,7 @@ void launch_iso_pre(cudaStream_t s, const PreArgs& a0) {
     a.two_rd = 2.0 / a.iso_dslope;
     a.m2c0 = -2.0 * a.iso_slopec / a.iso_dslope;
     a.s_max = (345.0 + a.iso_slopec / a.iso_dslope) * a.iso_dslope;
-    setup_kernel<<<min(64, (N * M + 255) / 256), 256, 0, s>>>(a.g, a.tables);
-    count_launch();
-    if (!check_launch("setup_kernel")) return;
+    if (!a.tables_ready) launch_setup_tables(s, a.g, a.dt_tracer, a.tables);
     if (a.eos == 5) {
         eos5_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, s>>>(ncell, nz, a.temp, a.salt, a.tau, a.maskT, a.g.zt,
                                                                    a.drdT, a.drdS);
