@@ -21,6 +21,8 @@
 // Slopes/diffusivities agree with the reference to ~1e-15 of their maximum (tests/), not bit for
 // bit (NumPy's SIMD tanh is not reproducible either).  The FLUXES are strict: given the stored Ai_*
 // and K_* they are bit-identical to the reference's expressions (flux_device.cuh).
+#include <algorithm>
+
 #include "common.cuh"
 #include "eos.cuh"
 #include "flux_device.cuh"
@@ -179,10 +181,32 @@ __global__ void __launch_bounds__(kPreBlock)
 iso_pre_kernel(const PreArgs a) {
     const int N = a.g.N, M = a.g.M, nz = a.g.nz;
     const int i = blockIdx.y;
-    const int p0 = blockIdx.x * kPreBlock;
     const Tables tb = tables_at(a.tables, N, M, nz);
+    const int plane_cells = M * nz;
+    const int nchunks = (plane_cells + kPreBlock - 1) / kPreBlock;
+    const int tau = *a.tau;
+    const double* __restrict__ T = a.temp + tau;
+    const double* __restrict__ S = a.salt + tau;
+    // Persistent over the chunks of its plane: while chunk n is computed (thousands of cycles of FP64
+    // work per warp) the lines chunk n+1 will touch are pulled into L2, so its loads cost an L2 hit
+    // instead of a DRAM round trip -- with ~12 resident warps per SM nothing else hides that latency.
+    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int p0 = chunk * kPreBlock;
+    {
+        const int pn = p0 + (int)gridDim.x * kPreBlock + (int)threadIdx.x;
+        if (pn < plane_cells) {
+            auto pf = [](const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); };
+            const size_t pl = (size_t)plane_cells;
+            const size_t cx = (size_t)i * pl + pn;
+            pf(T + cx * 3); pf(S + cx * 3);
+            pf(a.K_iso + cx); pf(a.maskT + cx); pf(a.maskU + cx); pf(a.maskV + cx); pf(a.maskW + cx);
+            if (i + 1 < N) { pf(T + (cx + pl) * 3); pf(S + (cx + pl) * 3); pf(a.K_iso + cx + pl); pf(a.maskW + cx + pl); pf(a.maskT + cx + pl); }
+            if (i >= 1) { pf(T + (cx - pl) * 3); pf(S + (cx - pl) * 3); pf(a.maskU + cx - pl); }
+            if (Eos<EOS>::kExpensive) { pf(a.drdT + cx); pf(a.drdS + cx); if (i + 1 < N) { pf(a.drdT + cx + pl); pf(a.drdS + cx + pl); } }
+        }
+    }
     const int p = p0 + threadIdx.x;
-    if (p >= M * nz) return;
+    if (p >= plane_cells) continue;
     const int j = p / nz;
     const int k = p - j * nz;
     const size_t plane = (size_t)M * nz;
@@ -196,21 +220,10 @@ iso_pre_kernel(const PreArgs a) {
     double fl[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};  // [tracer][east, north, top]
 
     if (inE || inN || inT) {
-        const int tau = *a.tau;
-        const double* __restrict__ T = a.temp + tau;
-        const double* __restrict__ S = a.salt + tau;
         auto ld = [](const double* f, size_t cell) { return __ldg(f + cell * 3); };
         const bool hasKm = k >= 1, hasKp = k < nz - 1;
         const int km = hasKm ? -1 : 0, kp = hasKp ? 1 : 0;  // clamped neighbours (pad_z_edges)
         const size_t ce = c + plane, cn = c + nz, cw = c - plane, cs = c - nz;
-        // Pull the neighbour planes / rows towards L1 now: their loads are scheduled late (register
-        // pressure) and would otherwise expose a DRAM round trip per face with only 12 resident warps.
-        {
-            auto pf = [](const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); };
-            pf(T + ce * 3); pf(S + ce * 3); pf(T + cn * 3); pf(S + cn * 3);
-            pf(a.K_iso + ce); pf(a.K_iso + cn);
-            if (inT) { pf(T + cw * 3); pf(S + cw * 3); pf(T + cs * 3); pf(S + cs * 3); }
-        }
         // metric table entries of this level / row / plane (read-only path, L1 resident)
         struct { Divisor d4zt; double rdzw, dzw, pabs; } L1, L0;
         {
@@ -468,6 +481,7 @@ iso_pre_kernel(const PreArgs a) {
 #pragma unroll
             for (int f = 0; f < 3; ++f) a.flux[t][f][c] = fl[t][f];
     }
+    }  // chunk loop
 }
 
 template <int EOS>
@@ -493,7 +507,9 @@ void launch_iso_pre(cudaStream_t s, const PreArgs& a0) {
         count_launch();
         if (!check_launch("eos5_kernel")) return;
     }
-    dim3 grid((M * nz + kPreBlock - 1) / kPreBlock, N);
+    const int nchunks = (M * nz + kPreBlock - 1) / kPreBlock;
+    const int per_plane = std::max(1, std::min(nchunks, (1332 + N - 1) / N));  // ~3 waves of 3 CTAs/SM in total
+    dim3 grid(per_plane, N);
     switch (a.eos) {
     case 1: launch_pre_eos<1>(s, a, grid); break;
     case 2: launch_pre_eos<2>(s, a, grid); break;
