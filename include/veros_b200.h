@@ -61,6 +61,13 @@ typedef struct VerosB200SolveDescriptor {
 } VerosB200SolveDescriptor;
 
 #define VEROS_B200_FLAG_SKEW 1 /* iso_diffusion: isoneutral_skew_diffusion (K1=-K_gm, K2=K_gm) */
+/* The arrays passed are an x-sub-slab (planes [i0, i1) of a wider local slab, via pointer offsets -- x is
+ * the slowest axis, so a sub-slab is contiguous).  Every output is idempotent under overlapping sub-slabs
+ * except the P_diss accumulation on the one-cell ring [1:-1] outside the interior (veros/core/diffusion.py:
+ * 15-35,41-62): with these flags the west (plane 1) / east (plane N-2) ring plane is left to the neighbouring
+ * sub-slab, whose interior it is.  Used to pipeline host<->device copies and to overlap the halo exchange. */
+#define VEROS_B200_FLAG_NO_WEST_RING 2
+#define VEROS_B200_FLAG_NO_EAST_RING 4
 
 /* Static (jit-constant) facts of the isoneutral ops: shapes and the settings of
  * veros/settings.py:24-91 that the path reads. */

@@ -26,7 +26,7 @@ def timeit(fn, states, n=20):
     return e0.elapsed_time(e1) / n * 1e3
 
 
-for name in sys.argv[1:] or ["bench_1M", "global_1deg"]:
+for name in sys.argv[1:] or ["bench_1M", "global_1deg", "global_4deg", "acc"]:
     st = synthetic.make_workload(name)
     cells = st["nx"] * st["ny"] * st["nz"]
     states = [IsoState.from_numpy(st, "cuda:0") for _ in range(2 if name != "bench_1M" else 3)]

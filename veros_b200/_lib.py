@@ -54,6 +54,7 @@ class IsoDescriptor(ctypes.Structure):
 
 HAS_B_EDGE, HAS_D_EDGE = 1, 2
 FLAG_SKEW = 1
+FLAG_NO_WEST_RING, FLAG_NO_EAST_RING = 2, 4
 
 _lib = None
 

@@ -192,6 +192,8 @@ void veros_b200_iso_diffusion_f64(void* stream, void** B, const char* opaque, si
     a.kbot = (const int32_t*)B[15];
     a.skew = (d->flags & VEROS_B200_FLAG_SKEW) ? 1 : 0;
     a.energy = energy ? 1 : 0;
+    a.skip_west_ring = (d->flags & VEROS_B200_FLAG_NO_WEST_RING) ? 1 : 0;
+    a.skip_east_ring = (d->flags & VEROS_B200_FLAG_NO_EAST_RING) ? 1 : 0;
     a.fluxes_ready = 0;
     a.dt_tracer = d->dt_tracer;
     a.grav = d->grav;
@@ -273,6 +275,8 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     a.kbot = (const int32_t*)B[19];
     a.skew = 0;
     a.energy = energy ? 1 : 0;
+    a.skip_west_ring = (d->flags & VEROS_B200_FLAG_NO_WEST_RING) ? 1 : 0;
+    a.skip_east_ring = (d->flags & VEROS_B200_FLAG_NO_EAST_RING) ? 1 : 0;
     a.fluxes_ready = 1;
     a.tables = p.tables;
     a.dt_tracer = d->dt_tracer;

@@ -56,6 +56,7 @@ struct DiffArgs {
     const uint8_t *maskT, *maskW;
     const int32_t* kbot;
     int skew, energy;
+    int skip_west_ring, skip_east_ring;  // sub-slab mode (VEROS_B200_FLAG_NO_*_RING)
     int fluxes_ready;  // the fused slope+flux kernel already filled the flux workspace
     double* tables;    // metric tables (tables.cuh), built by launch_setup_tables
     double dt_tracer, grav, rho_0;

@@ -174,6 +174,7 @@ update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch
     extern __shared__ double sm[];
     const int N = a.g.N, M = a.g.M, nz = a.g.nz;
     const int i = 1 + blockIdx.y;
+    if ((i == 1 && a.skip_west_ring) || (i == N - 2 && a.skip_east_ring)) return;  // a neighbouring sub-slab's interior
     const int j0 = 1 + blockIdx.x * cols;
     const int ncols = min(cols, (M - 1) - j0);
     const int tile = cols * pitch;

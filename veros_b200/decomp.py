@@ -74,3 +74,44 @@ def exchange_halos_x(fields, cyclic=True, group=None, level=None):
     for dst, buf in unpack:
         if dst is not buf:
             dst.copy_(buf)
+
+
+class OverlappedStepper:
+    """One isoneutral step of an x-slab with the halo exchange hidden behind interior compute.
+
+    The slab is processed as three sub-slabs (IsoState.subslab; bit-identical to the whole-slab step):
+    the two boundary strips (interior planes 2,3 and N-4,N-3: exactly what the neighbours need) go first
+    on a side stream, the NCCL send/recv of their temp/salt[taup1] planes follows on the communication
+    stream, and the remaining interior runs meanwhile on the caller's stream.  Replaces the sequence
+    "step, then enforce_boundaries(temp/salt[taup1])" of veros/core/thermodynamics.py:430-432,293-298.
+    """
+
+    def __init__(self, state, cyclic=True, group=None):
+        N = state.settings.nx + 4
+        if N < 12:
+            raise ValueError("slab too thin to overlap: needs at least 8 interior planes")
+        self.state, self.cyclic, self.group = state, cyclic, group
+        self.west = state.subslab(0, 6)
+        self.east = state.subslab(N - 6, N)
+        self.mid = state.subslab(2, N - 2)
+        for sub in (self.west, self.east):  # run concurrently with `mid`: private scratch
+            sub._parent = None
+        self.s_strip = torch.cuda.Stream(state.device)
+        self.s_comm = torch.cuda.Stream(state.device)
+        self.ev_strips = torch.cuda.Event()
+
+    def step(self):
+        from . import isoneutral
+
+        vs = self.state.variables
+        cur = torch.cuda.current_stream(self.state.device)
+        self.s_strip.wait_stream(cur)
+        with torch.cuda.stream(self.s_strip):
+            isoneutral.isoneutral_step(self.west)
+            isoneutral.isoneutral_step(self.east)
+            self.ev_strips.record(self.s_strip)
+        with torch.cuda.stream(self.s_comm):
+            self.s_comm.wait_event(self.ev_strips)
+            exchange_halos_x([vs.temp, vs.salt], cyclic=self.cyclic, group=self.group, level=int(vs.taup1_host))
+        isoneutral.isoneutral_step(self.mid)
+        cur.wait_stream(self.s_comm)

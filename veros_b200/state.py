@@ -49,6 +49,7 @@ class IsoState:
         self.device = device
         self._workspace = None
         self._dummy = torch.zeros(8, dtype=torch.float64, device=device)
+        self.ring_flags = 0  # VEROS_B200_FLAG_NO_WEST_RING / _NO_EAST_RING for x-sub-slab views
 
     # ---- construction --------------------------------------------------------------------------
     @classmethod
@@ -72,6 +73,7 @@ class IsoState:
         put("kbot", st["kbot"], np.int32)
         for name in ("tau", "taup1"):
             put(name, np.array([int(st[name])]), np.int32)
+            setattr(vs, name + "_host", int(st[name]))  # host copy for plumbing (halo packing)
         settings = SimpleNamespace(**{k: st[k] for k in SETTINGS})
         settings.eq_of_state_type = int(settings.eq_of_state_type)
         settings.enable_conserve_energy = bool(settings.enable_conserve_energy)
@@ -112,14 +114,41 @@ class IsoState:
     # ---- helpers --------------------------------------------------------------------------------
     def to_numpy(self, names=None):
         vs = self.variables
-        names = names or [n for n in vars(vs)]
+        names = names or [n for n in vars(vs) if not n.endswith("_host")]
         out = {}
         for n in names:
             t = getattr(vs, n)
             out[n] = t.cpu().numpy()
         return out
 
+    def subslab(self, i0, i1):
+        """View of the x-planes [i0, i1) (ghost planes included: the view's interior is [i0+2, i1-2)).
+        x is the slowest axis, so every sliced array stays contiguous and the ops run on it unchanged.
+        Interior sub-slabs of a wider slab get the ring flags so that P_diss is accumulated exactly once
+        (include/veros_b200.h, VEROS_B200_FLAG_NO_WEST_RING)."""
+        from . import _lib
+
+        N = self.settings.nx + 4
+        if not (0 <= i0 and i1 <= N and i1 - i0 >= 5):
+            raise ValueError(f"bad sub-slab [{i0}, {i1}) of {N} planes")
+        vs = Variables()
+        for name, t in vars(self.variables).items():
+            if name in ("tau", "taup1", "tau_host", "taup1_host") or name in METRICS_Y or name in METRICS_Z:
+                setattr(vs, name, t)
+            else:
+                setattr(vs, name, t[i0:i1])
+        settings = SimpleNamespace(**vars(self.settings))
+        settings.nx = (i1 - i0) - 4
+        sub = IsoState(vs, settings, self.device)
+        sub._dummy = self._dummy
+        sub.ring_flags = (0 if i0 == 0 else _lib.FLAG_NO_WEST_RING) | (0 if i1 == N else _lib.FLAG_NO_EAST_RING)
+        sub._parent = self
+        return sub
+
     def workspace(self, nbytes):
+        parent = getattr(self, "_parent", None)
+        if parent is not None:  # sub-slabs run one after the other on a stream: share the parent's scratch
+            return parent.workspace(nbytes)
         n = max(8, (int(nbytes) + 7) // 8)
         if self._workspace is None or self._workspace.numel() < n:
             self._workspace = torch.empty(n, dtype=torch.float64, device=self.device)
