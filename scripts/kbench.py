@@ -30,7 +30,12 @@ for name in sys.argv[1:] or ["bench_1M", "global_1deg", "global_4deg", "acc"]:
     st = synthetic.make_workload(name)
     cells = st["nx"] * st["ny"] * st["nz"]
     states = [IsoState.from_numpy(st, "cuda:0") for _ in range(2 if name != "bench_1M" else 3)]
-    t_step = timeit(isoneutral.isoneutral_step, states)
+    plans = {id(s): isoneutral.StepPlan(s) for s in states}
+    t_step = timeit(lambda s: plans[id(s)](), states)
+    for pl in plans.values():
+        pl.capture()
+    t_graph = timeit(lambda s: plans[id(s)](), states)
+    print(f"{name}: step via CUDA graph {t_graph:8.1f} us")
     t_pre = timeit(isoneutral.isoneutral_diffusion_pre, states)
     t_dT = timeit(lambda s: isoneutral.isoneutral_diffusion(s, s.variables.temp, True), states)
     print(f"{name}: step {t_step:8.1f} us  ({cells / t_step / 1e3:.2f} Gcell/s, "

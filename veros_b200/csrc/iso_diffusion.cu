@@ -15,6 +15,8 @@
 // operation here, in the reference's order, and the column solve replays dgtsv (tdma_device.cuh),
 // so on identical inputs the outputs are bit-identical to the reference's NumPy backend.  Divisions
 // by grid metrics use correctly rounded reciprocals tabulated once per CTA (strict.cuh).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "strict.cuh"
 #include "tdma_device.cuh"
@@ -385,6 +387,7 @@ void launch_update(cudaStream_t s, const DiffArgs& a, const Scratch& f) {
     const int pitch = nz | 1;
     const int narr = SKEW ? 0 : 3 + NTR;
     int cols = max(1, 640 / nz);
+    if (const char* e = getenv("VEROS_B200_UPD_CELLS")) cols = max(1, atoi(e) / nz);  // tuning knob (tile cells)
     cols = min(cols, M - 2);
     const int want_tiles = 4 * 148;  // small grids: spread over the SMs
     const int rows = N - 2;

@@ -96,22 +96,24 @@ class OverlappedStepper:
         self.mid = state.subslab(2, N - 2)
         for sub in (self.west, self.east):  # run concurrently with `mid`: private scratch
             sub._parent = None
+        from . import isoneutral
+
+        state.workspace(isoneutral.step_workspace_bytes(state))  # `mid` shares it; keep its address stable
+        self.plans = [isoneutral.StepPlan(s) for s in (self.west, self.east, self.mid)]
         self.s_strip = torch.cuda.Stream(state.device)
         self.s_comm = torch.cuda.Stream(state.device)
         self.ev_strips = torch.cuda.Event()
 
     def step(self):
-        from . import isoneutral
-
         vs = self.state.variables
         cur = torch.cuda.current_stream(self.state.device)
         self.s_strip.wait_stream(cur)
         with torch.cuda.stream(self.s_strip):
-            isoneutral.isoneutral_step(self.west)
-            isoneutral.isoneutral_step(self.east)
+            self.plans[0]()
+            self.plans[1]()
             self.ev_strips.record(self.s_strip)
         with torch.cuda.stream(self.s_comm):
             self.s_comm.wait_event(self.ev_strips)
             exchange_halos_x([vs.temp, vs.salt], cyclic=self.cyclic, group=self.group, level=int(vs.taup1_host))
-        isoneutral.isoneutral_step(self.mid)
+        self.plans[2]()
         cur.wait_stream(self.s_comm)

@@ -40,6 +40,9 @@ class HostStepper:
         # interior planes [2, N-2) split into `slabs` owned ranges [a, b); each computes on the view
         # [a-2, b+2) (clamped to the slab), is fed by the planes up to b+2 and returns its owned planes
         N = self.state.settings.nx + 4
+        # sub-slabs share the parent's scratch: size it once for the largest user so that the pointers
+        # captured by the plans stay valid
+        self.state.workspace(isoneutral.step_workspace_bytes(self.state))
         slabs = max(1, min(int(slabs), N - 4))
         cuts = [2 + (N - 4) * s // slabs for s in range(slabs + 1)]
         self.parts = []
@@ -49,7 +52,7 @@ class HostStepper:
             lo, hi = (0 if s == 0 else a - 2), (N if s == slabs - 1 else b + 2)
             own_lo, own_hi = (0 if s == 0 else a), (N if s == slabs - 1 else b)
             sub = self.state if slabs == 1 else self.state.subslab(lo, hi)
-            self.parts.append(dict(sub=sub, feed=(fed, hi), own=(own_lo, own_hi),
+            self.parts.append(dict(sub=sub, plan=isoneutral.StepPlan(sub), feed=(fed, hi), own=(own_lo, own_hi),
                                    ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event()))
             fed = hi
         dev = self.state.device
@@ -75,7 +78,7 @@ class HostStepper:
                 part["ev_in"].record(self.s_in)
         for part in self.parts:
             cur.wait_event(part["ev_in"])
-            isoneutral.isoneutral_step(part["sub"])
+            part["plan"]()
             part["ev_done"].record(cur)
             lo, hi = part["own"]
             with torch.cuda.stream(self.s_out):
