@@ -154,6 +154,12 @@ int veros_b200_last_error(void);
 const char* veros_b200_last_error_string(void);
 void veros_b200_clear_error(void);
 
+/* Measurement hook: while set (n >= 4, events created by the caller), veros_b200_iso_step_f64 records
+ * events[0] on its stream before its first kernel, [1] before the slope+flux kernel, [2] after it and
+ * [3] after the update kernel, so a benchmark can time the dominant kernel inside the fused call with
+ * CUDA events.  Pass NULL / 0 to clear.  Not for concurrent use from several threads. */
+void veros_b200_profile_events(void** events, int n);
+
 int veros_b200_abi_version(void);
 /* sizeof() of descriptor 0 = Tridiag, 1 = Solve, 2 = Iso as compiled into the library. */
 size_t veros_b200_descriptor_size(int which);

@@ -28,6 +28,7 @@ HELPERS = (
     "veros_b200_abi_version",
     "veros_b200_descriptor_size",
     "veros_b200_launch_count",
+    "veros_b200_profile_events",
 )
 
 
@@ -85,6 +86,8 @@ def lib():
     L.veros_b200_descriptor_size.restype = ctypes.c_size_t
     L.veros_b200_descriptor_size.argtypes = [ctypes.c_int]
     L.veros_b200_launch_count.restype = ctypes.c_ulonglong
+    L.veros_b200_profile_events.restype = None
+    L.veros_b200_profile_events.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
     if L.veros_b200_abi_version() != ABI_VERSION:
         raise RuntimeError("libveros_b200.so ABI version mismatch; rebuild with `python -m veros_b200.build --force`")
     for which, cls in enumerate((TridiagDescriptor, SolveDescriptor, IsoDescriptor)):

@@ -83,6 +83,12 @@ static Grid make_grid(const VerosB200IsoDescriptor* d, void* dxt, void* dxu, voi
     return g;
 }
 
+cudaEvent_t* g_prof_events = nullptr;
+int g_prof_n = 0;
+void prof_mark(cudaStream_t s, int q) {
+    if (g_prof_events && q < g_prof_n) cudaEventRecord(g_prof_events[q], s);
+}
+
 static size_t tabs_doubles(const VerosB200IsoDescriptor* d) {
     return (tables_doubles(d->nx_tot, d->ny_tot, d->nz) + 1) & ~(size_t)1;  // keep 16 B alignment behind it
 }
@@ -238,6 +244,7 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     p.dt_tracer = d->dt_tracer;
     p.drdT = p.tables + tabs_doubles(d);
     p.drdS = p.drdT + n3;
+    prof_mark(s, 0);
     launch_setup_tables(s, p.g, d->dt_tracer, p.tables);
     if (veros_b200_last_error()) return;
     p.with_flux = 1;
@@ -247,7 +254,7 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     p.K_iso_steep = d->K_iso_steep;
     p.iso_slopec = d->iso_slopec;
     p.iso_dslope = d->iso_dslope;
-    launch_iso_pre(s, p);
+    launch_iso_pre(s, p, /*profile=*/true);
     if (veros_b200_last_error()) return;
 
     DiffArgs a;
@@ -283,6 +290,12 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     a.grav = d->grav;
     a.rho_0 = d->rho_0;
     launch_iso_diffusion_ws(s, a, ws);
+    prof_mark(s, 3);
+}
+
+void veros_b200_profile_events(void** events, int n) {
+    g_prof_events = reinterpret_cast<cudaEvent_t*>(events);
+    g_prof_n = events ? n : 0;
 }
 
 size_t veros_b200_iso_pre_workspace_bytes(const char* opaque, size_t len) {

@@ -63,7 +63,8 @@ struct DiffArgs {
 };
 
 // ---- launchers (one per translation unit) -----------------------------------------------------
-void launch_iso_pre(cudaStream_t s, const PreArgs& a);
+void launch_iso_pre(cudaStream_t s, const PreArgs& a, bool profile = false);
+void prof_mark(cudaStream_t s, int q);  // api.cu: records the q-th profiling event if a benchmark installed some
 size_t diffusion_workspace_doubles(int N, int M, int nz, int ntr);
 void launch_iso_diffusion_ws(cudaStream_t s, const DiffArgs& a, double* workspace);
 void launch_solve_implicit(cudaStream_t s, int ncol, int nz, const double* a, const double* b, const double* c,

@@ -492,7 +492,7 @@ static void launch_pre_eos(cudaStream_t s, const PreArgs& a, dim3 grid) {
         iso_pre_kernel<EOS, false><<<grid, kPreBlock, 0, s>>>(a);
 }
 
-void launch_iso_pre(cudaStream_t s, const PreArgs& a0) {
+void launch_iso_pre(cudaStream_t s, const PreArgs& a0, bool profile) {
     PreArgs a = a0;
     const int N = a.g.N, M = a.g.M, nz = a.g.nz;
     const size_t ncell = (size_t)N * M * nz;
@@ -510,6 +510,7 @@ void launch_iso_pre(cudaStream_t s, const PreArgs& a0) {
     const int nchunks = (M * nz + kPreBlock - 1) / kPreBlock;
     const int per_plane = std::max(1, std::min(nchunks, (1332 + N - 1) / N));  // ~3 waves of 3 CTAs/SM in total
     dim3 grid(per_plane, N);
+    if (profile) prof_mark(s, 1);
     switch (a.eos) {
     case 1: launch_pre_eos<1>(s, a, grid); break;
     case 2: launch_pre_eos<2>(s, a, grid); break;
@@ -517,6 +518,7 @@ void launch_iso_pre(cudaStream_t s, const PreArgs& a0) {
     case 4: launch_pre_eos<4>(s, a, grid); break;
     default: launch_pre_eos<5>(s, a, grid); break;
     }
+    if (profile) prof_mark(s, 2);
     count_launch();
     check_launch("iso_pre_kernel");
 }
