@@ -224,6 +224,8 @@ def main():
     plans = [isoneutral.StepPlan(s) for s in states]  # argument marshalling done once, as under XLA
     overlap = world > 1 and (args.overlap == "on" or (args.overlap == "auto" and cells >= 3_000_000))
     steppers = [decomp.OverlappedStepper(s, cyclic=cyclic) for s in states] if overlap else None
+    exchanges = [decomp.TracerHaloExchange([s.variables.temp, s.variables.salt], level=int(st["taup1"]), cyclic=cyclic)
+                 for s in states] if (world > 1 and not overlap) else None
 
     def step(s):
         q = states.index(s)
@@ -233,8 +235,7 @@ def main():
             steppers[q].step()  # boundary strips -> NCCL exchange || interior
         else:
             plans[q]()
-            vs = s.variables
-            decomp.exchange_halos_x([vs.temp, vs.salt], cyclic=cyclic, level=int(st["taup1"]))
+            exchanges[q]()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

@@ -154,6 +154,14 @@ int veros_b200_last_error(void);
 const char* veros_b200_last_error_string(void);
 void veros_b200_clear_error(void);
 
+/* Multi-GPU plumbing (not a custom call): gather (mode 0) the west/east interior edge planes [2,4) and
+ * [N-4,N-2) of up to 4 fields into contiguous buffers, or scatter (mode 1) received buffers into the ghost
+ * planes [0,2) and [N-2,N).  Fields are (N,M,nz[,nlev]) float64; `level` selects the time level of tracers
+ * (nlev = 3) -- what veros/core/thermodynamics.py:293-298 exchanges.  A NULL buffer skips that side.
+ * Buffer layout: field-major, 2*M*nz doubles per field. */
+void veros_b200_halo_pack_unpack(void* stream, int mode, void** fields, int nfields, int nx_tot, int ny_tot, int nz,
+                                 int nlev, int level, void* west_buf, void* east_buf);
+
 /* Measurement hook: while set (n >= 4, events created by the caller), veros_b200_iso_step_f64 records
  * events[0] on its stream before its first kernel, [1] before the slope+flux kernel, [2] after it and
  * [3] after the update kernel, so a benchmark can time the dominant kernel inside the fused call with

@@ -29,6 +29,7 @@ HELPERS = (
     "veros_b200_descriptor_size",
     "veros_b200_launch_count",
     "veros_b200_profile_events",
+    "veros_b200_halo_pack_unpack",
 )
 
 
@@ -86,6 +87,10 @@ def lib():
     L.veros_b200_descriptor_size.restype = ctypes.c_size_t
     L.veros_b200_descriptor_size.argtypes = [ctypes.c_int]
     L.veros_b200_launch_count.restype = ctypes.c_ulonglong
+    L.veros_b200_halo_pack_unpack.restype = None
+    L.veros_b200_halo_pack_unpack.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_void_p, ctypes.c_void_p]
     L.veros_b200_profile_events.restype = None
     L.veros_b200_profile_events.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
     if L.veros_b200_abi_version() != ABI_VERSION:

@@ -21,6 +21,7 @@ SOURCES = {
     "tdma.cu": ["-fmad=false"],
     "iso_pre.cu": [],
     "iso_diffusion.cu": [],
+    "halo.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

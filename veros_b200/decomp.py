@@ -76,6 +76,62 @@ def exchange_halos_x(fields, cyclic=True, group=None, level=None):
             dst.copy_(buf)
 
 
+class TracerHaloExchange:
+    """The halo exchange of `fields` (same shape, (N,M,nz,3) tracers with `level`, or (N,M,nz) fields) on
+    CUDA tensors: one pack launch, one batched NCCL send/recv pair per neighbour, one unpack launch --
+    instead of a torch slicing/copy op per field, direction and side (launch bound at these sizes)."""
+
+    def __init__(self, fields, level=None, cyclic=True, group=None):
+        import ctypes
+
+        from . import _lib
+
+        f0 = fields[0]
+        if not all(f.is_cuda and f.is_contiguous() and f.shape == f0.shape and f.dtype == torch.float64 for f in fields):
+            raise ValueError("fields must be contiguous float64 CUDA tensors of one shape")
+        if (f0.dim() == 4) != (level is not None):
+            raise ValueError("4-D tracers need a time level, 3-D fields must not have one")
+        self.fields, self.cyclic, self.group = list(fields), cyclic, group
+        self.N, self.M, self.nz = f0.shape[:3]
+        self.nlev, self.level = (f0.shape[3], int(level)) if level is not None else (1, 0)
+        n = 2 * self.M * self.nz * len(fields)
+        self.send_w, self.send_e, self.recv_w, self.recv_e = (torch.empty(n, dtype=torch.float64, device=f0.device) for _ in range(4))
+        self._ptrs = (ctypes.c_void_p * len(fields))(*[f.data_ptr() for f in fields])
+        self._fn = _lib.lib().veros_b200_halo_pack_unpack
+        self._check = _lib.check_error
+        self._vp = ctypes.c_void_p
+
+    def _launch(self, mode, west, east):
+        s = torch.cuda.current_stream(self.fields[0].device).cuda_stream
+        self._fn(self._vp(s), mode, self._ptrs, len(self.fields), self.N, self.M, self.nz, self.nlev, self.level,
+                 self._vp(west.data_ptr()) if west is not None else None,
+                 self._vp(east.data_ptr()) if east is not None else None)
+
+    def __call__(self):
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        west, east = neighbours(rank, world, self.cyclic)
+        if world == 1:
+            if self.cyclic:  # wrap around locally: east edge -> west ghosts, west edge -> east ghosts
+                self._launch(0, self.send_w, self.send_e)
+                self._launch(1, self.send_e, self.send_w)
+            return
+        self._launch(0, self.send_w if west is not None else None, self.send_e if east is not None else None)
+        ops = []  # posting order: see exchange_halos_x
+        if east is not None:
+            ops.append(dist.P2POp(dist.isend, self.send_e, east, self.group))
+        if west is not None:
+            ops.append(dist.P2POp(dist.isend, self.send_w, west, self.group))
+        if west is not None:
+            ops.append(dist.P2POp(dist.irecv, self.recv_w, west, self.group))
+        if east is not None:
+            ops.append(dist.P2POp(dist.irecv, self.recv_e, east, self.group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        self._launch(1, self.recv_w if west is not None else None, self.recv_e if east is not None else None)
+        self._check("halo exchange")
+
+
 class OverlappedStepper:
     """One isoneutral step of an x-slab with the halo exchange hidden behind interior compute.
 
@@ -100,6 +156,8 @@ class OverlappedStepper:
 
         state.workspace(isoneutral.step_workspace_bytes(state))  # `mid` shares it; keep its address stable
         self.plans = [isoneutral.StepPlan(s) for s in (self.west, self.east, self.mid)]
+        vs = state.variables
+        self.exchange = TracerHaloExchange([vs.temp, vs.salt], level=vs.taup1_host, cyclic=cyclic, group=group)
         self.s_strip = torch.cuda.Stream(state.device)
         self.s_comm = torch.cuda.Stream(state.device)
         self.ev_strips = torch.cuda.Event()
@@ -114,6 +172,6 @@ class OverlappedStepper:
             self.ev_strips.record(self.s_strip)
         with torch.cuda.stream(self.s_comm):
             self.s_comm.wait_event(self.ev_strips)
-            exchange_halos_x([vs.temp, vs.salt], cyclic=self.cyclic, group=self.group, level=int(vs.taup1_host))
+            self.exchange()
         self.plans[2]()
         cur.wait_stream(self.s_comm)
