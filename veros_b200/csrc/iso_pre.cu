@@ -22,6 +22,7 @@
 // bit (NumPy's SIMD tanh is not reproducible either).  The FLUXES are strict: given the stored Ai_*
 // and K_* they are bit-identical to the reference's expressions (flux_device.cuh).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "eos.cuh"
@@ -176,9 +177,13 @@ void launch_setup_tables(cudaStream_t s, const Grid& g, double dt_tracer, double
 
 constexpr int kPreBlock = 128;
 
-template <int EOS, bool FLUX>
+// FACES selects which faces this launch produces (bit 0 east, bit 1 north, bit 2 top).  Splitting the
+// 16 slopes over two launches (east+north / top) halves the live state per thread, which raises the
+// register-limited occupancy of this latency-bound kernel; the price is a second read of T and S.
+template <int EOS, bool FLUX, int FACES>
 __global__ void __launch_bounds__(kPreBlock)
 iso_pre_kernel(const PreArgs a) {
+    constexpr bool doE = (FACES & 1) != 0, doN = (FACES & 2) != 0, doT = (FACES & 4) != 0;
     const int N = a.g.N, M = a.g.M, nz = a.g.nz;
     const int i = blockIdx.y;
     const Tables tb = tables_at(a.tables, N, M, nz);
@@ -212,11 +217,11 @@ iso_pre_kernel(const PreArgs a) {
     const size_t plane = (size_t)M * nz;
     const size_t c = (size_t)i * plane + p;
 
-    if (k == nz - 1) a.K_33[c] = 0.0;  // isoneutral.py:225, whole array including ghost cells
+    if (doT && k == nz - 1) a.K_33[c] = 0.0;  // isoneutral.py:225, whole array including ghost cells
 
-    const bool inE = (i >= 1 && i < N - 2 && j >= 2 && j < M - 2);
-    const bool inN = (i >= 2 && i < N - 2 && j >= 1 && j < M - 2);
-    const bool inT = (i >= 2 && i < N - 2 && j >= 2 && j < M - 2 && k < nz - 1);
+    const bool inE = doE && (i >= 1 && i < N - 2 && j >= 2 && j < M - 2);
+    const bool inN = doN && (i >= 2 && i < N - 2 && j >= 1 && j < M - 2);
+    const bool inT = doT && (i >= 2 && i < N - 2 && j >= 2 && j < M - 2 && k < nz - 1);
     double fl[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};  // [tracer][east, north, top]
 
     if (inE || inN || inT) {
@@ -477,19 +482,37 @@ iso_pre_kernel(const PreArgs a) {
     }
     if (FLUX) {
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
-#pragma unroll
-            for (int f = 0; f < 3; ++f) a.flux[t][f][c] = fl[t][f];
+        for (int t = 0; t < 2; ++t) {
+            if (doE) a.flux[t][0][c] = fl[t][0];
+            if (doN) a.flux[t][1][c] = fl[t][1];
+            if (doT) a.flux[t][2][c] = fl[t][2];
+        }
     }
     }  // chunk loop
+}
+
+template <int EOS, bool FLUX>
+static void launch_pre_variant(cudaStream_t s, const PreArgs& a, dim3 grid) {
+    static const bool force_single = getenv("VEROS_B200_PRE_SINGLE") != nullptr;  // tuning knob
+    // measured (profiles/): the split is +3 % on the 1 degree grid, neutral at 1 M cells, and costs one
+    // launch, which small grids cannot afford
+    const bool single = force_single || (size_t)a.g.N * a.g.M * a.g.nz < 500000;
+    if (single) {
+        iso_pre_kernel<EOS, FLUX, 7><<<grid, kPreBlock, 0, s>>>(a);
+        count_launch();
+    } else {
+        iso_pre_kernel<EOS, FLUX, 3><<<grid, kPreBlock, 0, s>>>(a);
+        iso_pre_kernel<EOS, FLUX, 4><<<grid, kPreBlock, 0, s>>>(a);
+        count_launch(2);
+    }
 }
 
 template <int EOS>
 static void launch_pre_eos(cudaStream_t s, const PreArgs& a, dim3 grid) {
     if (a.with_flux)
-        iso_pre_kernel<EOS, true><<<grid, kPreBlock, 0, s>>>(a);
+        launch_pre_variant<EOS, true>(s, a, grid);
     else
-        iso_pre_kernel<EOS, false><<<grid, kPreBlock, 0, s>>>(a);
+        launch_pre_variant<EOS, false>(s, a, grid);
 }
 
 void launch_iso_pre(cudaStream_t s, const PreArgs& a0, bool profile) {
@@ -519,7 +542,6 @@ void launch_iso_pre(cudaStream_t s, const PreArgs& a0, bool profile) {
     default: launch_pre_eos<5>(s, a, grid); break;
     }
     if (profile) prof_mark(s, 2);
-    count_launch();
     check_launch("iso_pre_kernel");
 }
 
