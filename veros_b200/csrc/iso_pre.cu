@@ -10,11 +10,11 @@
 //
 // This kernel is bound by the FP64 pipe and by instruction issue, not by HBM (ncu: profiles/), so
 // the design goal is instructions per cell:
-//   * every division by a grid metric is a multiplication by a reciprocal tabulated once per CTA
-//     in shared memory (the same tables hold the correctly rounded reciprocals the strict flux
+//   * every division by a grid metric is a multiplication by a reciprocal tabulated once per call
+//     (tables.cuh; the same tables hold the correctly rounded reciprocals the strict flux
 //     arithmetic needs, strict.cuh);
-//   * 0.5*(1+tanh(x)) = 1/(1+exp(-2x)) costs one branch-free exp (64-entry 2^(j/64) table in
-//     shared memory + degree-5 polynomial) and one Newton reciprocal seeded by rcp.approx;
+//   * 0.5*(1+tanh(x)) = 1/(1+exp(-2x)) costs one branch-free, table-free exp (degree-12 polynomial)
+//     and one Newton reciprocal seeded by rcp.approx;
 //   * slope denominators use the same branch-free reciprocal; the four x- and four y-slopes of a
 //     top face share two of them;
 //   * masks enter as selects folded into the metric factors, never as int->double conversions.
@@ -38,24 +38,6 @@ using strict::make_divisor;
 
 constexpr double kEps = 1e-20;  // isoneutral.py:28
 
-__device__ const double g_exp2_table[64] = {
-    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
-    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
-    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
-    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
-    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
-    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
-    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
-    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
-    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
-    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
-    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
-    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
-    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
-    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
-    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
-    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
-
 // 1/x for normal finite x with 1/x normal: rcp.approx (>= 20 good bits) + one cubic Newton step.
 __device__ __forceinline__ double rcp_fast(double x) {
     double r;
@@ -65,23 +47,33 @@ __device__ __forceinline__ double rcp_fast(double x) {
     return fma(r, t, r);
 }
 
-// exp(u) for u in [-700, 700], relative error < 4e-16, no branches.
-//   u = (64 n + j) ln2/64 + r,  exp(u) = 2^n * 2^(j/64) * (1 + r q(r)),  |r| <= ln2/128
+// exp(u) for u in [-700, 700], relative error < 3e-16, no branches, no table:
+//   u = n ln2 + r, |r| <= ln2/2;  exp(r) by its degree-12 Taylor polynomial (|r|^13/13! < 2e-16).
+// (A 64-entry 2^(j/64) table with a degree-5 polynomial needs 6 fewer FP64 instructions but puts a
+// dependent L1 load into each of the 16 taper chains of a cell; this kernel is latency bound.)
 __device__ __forceinline__ double exp_fast(double u) {
     constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer in the low word
-    double t = fma(u, 0x1.71547652b82fep+6, kMagic);
-    const int ni = __double2loint(t);
+    double t = fma(u, 0x1.71547652b82fep+0, kMagic);
+    const int n = __double2loint(t);
     t -= kMagic;
-    double r = fma(t, -0x1.62e42fe000000p-7, u);
-    r = fma(t, -0x1.f473de6af278fp-36, r);
-    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    q = fma(q, r, 1.0 / 6.0);
-    q = fma(q, r, 0.5);
-    q = fma(q, r, 1.0);
-    const double p = r * q;
-    const double T = __ldg(&g_exp2_table[ni & 63]);
-    const double e = fma(T, p, T);
-    return __hiloint2double(__double2hiint(e) + ((ni >> 6) << 20), __double2loint(e));
+    double r = fma(t, -0x1.62e42fefa3800p-1, u);
+    r = fma(t, -0x1.ef35793c76730p-45, r);
+    // Horner on purpose: an Estrin split (depth 4 instead of 12, 3 more instructions, 9 more live values)
+    // measured 7-15 % slower -- this kernel pays for instructions and registers, not for chain depth.
+    double p = 1.0 / 479001600.0;
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
 struct Taper {
