@@ -15,6 +15,7 @@
 // operation here, in the reference's order, and the column solve replays dgtsv (tdma_device.cuh),
 // so on identical inputs the outputs are bit-identical to the reference's NumPy backend.  Divisions
 // by grid metrics use correctly rounded reciprocals tabulated once per CTA (strict.cuh).
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -169,61 +170,90 @@ struct Scratch {
 
 constexpr int kUpdBlock = 128;
 
-template <int NTR, bool SKEW, bool ENERGY>
-__global__ void __launch_bounds__(kUpdBlock, 6)
-update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch, const double fac_diss,
-              const double gr) {
-    extern __shared__ double sm[];
-    const int N = a.g.N, M = a.g.M, nz = a.g.nz;
-    const int i = 1 + blockIdx.y;
-    if ((i == 1 && a.skip_west_ring) || (i == N - 2 && a.skip_east_ring)) return;  // a neighbouring sub-slab's interior
-    const int j0 = 1 + blockIdx.x * cols;
-    const int ncols = min(cols, (M - 1) - j0);
+// ---- pieces of the update shared by the plain and the pipelined kernel ---------------------------------
+struct LevelTabs {        // per level, once per CTA
+    Divisor* ddzt;        // dzt[k]
+    Divisor* ddzw;        // dzw[k]
+    double* dt_dzw;       // dt_tracer / dzw[k]
+};
+struct TileBuf {          // one tile of whole columns in shared memory
+    double *L, *D, *U, *R[2];
+    Divisor *dcdxt, *dcdyt;  // cost[j]*dxt[i], cost[j]*dyt[j] per column
+    int* ksv;                // kbot - 1 per column
+};
+struct TileGeom {
+    int i, j0, ncols, ncells;
+    size_t base;
+    bool i_int;
+};
+struct UpdConst {
+    int N, M, nz, pitch, tau, taup1;
+    size_t plane;
+    double dt, fac_diss, gr;
+    Divisor ddt;
+};
+
+__device__ __forceinline__ TileBuf tile_buf_at(double* p, int cols, int pitch, int ntr) {
+    TileBuf b;
     const int tile = cols * pitch;
+    b.L = p;
+    b.D = b.L + tile;
+    b.U = b.D + tile;
+    b.R[0] = b.U + tile;
+    b.R[1] = b.R[0] + (ntr > 1 ? tile : 0);
+    b.dcdxt = reinterpret_cast<Divisor*>(b.R[0] + (size_t)ntr * tile);
+    b.dcdyt = b.dcdxt + cols;
+    b.ksv = reinterpret_cast<int*>(b.dcdyt + cols);
+    return b;
+}
 
-    double* L = sm;
-    double* D = L + tile;
-    double* U = D + tile;
-    double* R[2] = {U + tile, U + tile * 2};
-    double* tab = U + tile * (1 + NTR);
-    Divisor* ddzt = reinterpret_cast<Divisor*>(tab);             // dzt[k]
-    Divisor* ddzw = ddzt + nz;                                   // dzw[k]
-    double* dt_dzw = reinterpret_cast<double*>(ddzw + nz);       // dt_tracer / dzw[k]
-    Divisor* dcdxt = reinterpret_cast<Divisor*>(dt_dzw + nz);    // cost[j]*dxt[i]
-    Divisor* dcdyt = dcdxt + cols;                               // cost[j]*dyt[j]
-    int* ksv = reinterpret_cast<int*>(dcdyt + cols);             // kbot-1 per column
+__device__ __forceinline__ TileGeom tile_geom(const UpdConst& u, int i, int j0, int cols) {
+    TileGeom g;
+    g.i = i;
+    g.j0 = j0;
+    g.ncols = min(cols, (u.M - 1) - j0);
+    g.ncells = g.ncols * u.nz;
+    g.base = (size_t)i * u.plane + (size_t)j0 * u.nz;
+    g.i_int = (i >= 2 && i < u.N - 2);
+    return g;
+}
 
-    const double dt = a.dt_tracer;
-    for (int k = threadIdx.x; k < nz; k += kUpdBlock) {
-        ddzt[k] = make_divisor(a.g.dzt[k]);
-        ddzw[k] = make_divisor(a.g.dzw[k]);
-        dt_dzw[k] = strict::div(dt, a.g.dzw[k]);
+__device__ __forceinline__ void fill_level_tabs(const DiffArgs& a, const LevelTabs& lv, int nz, double dt, int tid, int nthr) {
+    for (int k = tid; k < nz; k += nthr) {
+        lv.ddzt[k] = make_divisor(a.g.dzt[k]);
+        lv.ddzw[k] = make_divisor(a.g.dzw[k]);
+        lv.dt_dzw[k] = strict::div(dt, a.g.dzw[k]);
     }
-    for (int q = threadIdx.x; q < ncols; q += kUpdBlock) {
-        const int j = j0 + q;
-        dcdxt[q] = make_divisor(mul(a.g.cost[j], a.g.dxt[i]));
-        dcdyt[q] = make_divisor(mul(a.g.cost[j], a.g.dyt[j]));
-        ksv[q] = a.kbot[i * M + j] - 1;
+}
+
+__device__ __forceinline__ void fill_tile_tabs(const DiffArgs& a, const UpdConst& u, const TileBuf& b, const TileGeom& g,
+                                               int tid, int nthr) {
+    for (int q = tid; q < g.ncols; q += nthr) {
+        const int j = g.j0 + q;
+        b.dcdxt[q] = make_divisor(mul(a.g.cost[j], a.g.dxt[g.i]));
+        b.dcdyt[q] = make_divisor(mul(a.g.cost[j], a.g.dyt[j]));
+        b.ksv[q] = a.kbot[g.i * u.M + j] - 1;
     }
-    __syncthreads();
+}
 
-    const Divisor ddt = make_divisor(dt);
-    const int tau = *a.tau, taup1 = *a.taup1;
-    const size_t plane = (size_t)M * nz;
-    const size_t base = (size_t)i * plane + (size_t)j0 * nz;
-    const int ncells = ncols * nz;
-    const bool i_int = (i >= 2 && i < N - 2);
-
+// phase B: explicit flux divergence, tracer + tendency update, right-hand sides, matrix, T-point dissipation
+template <int NTR, bool SKEW, bool ENERGY>
+__device__ __forceinline__ void phase_b(const DiffArgs& a, const Scratch& f, const UpdConst& u, const LevelTabs& lv,
+                                        const TileBuf& b, const TileGeom& g, int tid, int nthr) {
+    const int N = u.N, M = u.M, nz = u.nz, pitch = u.pitch, tau = u.tau, taup1 = u.taup1;
+    const size_t plane = u.plane;
+    const double dt = u.dt, fac_diss = u.fac_diss;
+    (void)N;
     // ---- phase B --------------------------------------------------------------------------------
     // Every global load of a (cell, tracer) pair is issued before the first dependent store: the
     // compiler must keep loads behind earlier stores that might alias, so interleaving them would
     // serialise four memory round trips per cell.
-    for (int idx = threadIdx.x; idx < ncells; idx += kUpdBlock) {
+    for (int idx = tid; idx < g.ncells; idx += nthr) {
         const int q = idx / nz, k = idx - q * nz;
-        const int j = j0 + q;
-        const bool interior = i_int && j >= 2 && j < M - 2;
+        const int j = g.j0 + q;
+        const bool interior = g.i_int && j >= 2 && j < M - 2;
         if (!interior && !ENERGY) continue;
-        const size_t c = base + idx;
+        const size_t c = g.base + idx;
         const int s = q * pitch + k;
         const double mT = interior ? (double)a.maskT[c] : 0.0;
         double k33 = 0.0, k33m = 0.0;
@@ -254,63 +284,69 @@ update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch
             }
             // arithmetic + stores
             if (interior) {
-                double e = mul(mT, add(strict::div(sub(fe_c, fe_w), dcdxt[q]), strict::div(sub(fn_c, fn_s), dcdyt[q])));
+                double e = mul(mT, add(strict::div(sub(fe_c, fe_w), b.dcdxt[q]), strict::div(sub(fn_c, fn_s), b.dcdyt[q])));
                 if (k == 0)
-                    e = add(e, strict::div(mul(mT, ft_c), ddzt[0]));
+                    e = add(e, strict::div(mul(mT, ft_c), lv.ddzt[0]));
                 else
-                    e = add(e, strict::div(mul(mT, sub(ft_c, ft_m)), ddzt[k]));
+                    e = add(e, strict::div(mul(mT, sub(ft_c, ft_m)), lv.ddzt[k]));
                 a.t[t].dtracer[c] = add(dtr_old, e);        // diffusion.py:196
                 const double v = add(tr_old, mul(dt, e));  // diffusion.py:197
                 a.t[t].tr[c * 3 + taup1] = v;
-                if (!SKEW) R[t][s] = v;
+                if (!SKEW) b.R[t][s] = v;
             }
             if (ENERGY) {  // compute_dissipation, veros/core/diffusion.py:15-35 (on [1:-1, 1:-1])
                 const double gx = add(mul(sub(xe, xc), fe_c), mul(sub(xc, xw), fe_w));
                 const double gy = add(mul(sub(xn, xc), fn_c), mul(sub(xc, xs), fn_s));
-                f.diss[t][c] = add(strict::div(mul(fac_diss, gx), dcdxt[q]), strict::div(mul(fac_diss, gy), dcdyt[q]));
+                f.diss[t][c] = add(strict::div(mul(fac_diss, gx), b.dcdxt[q]), strict::div(mul(fac_diss, gy), b.dcdyt[q]));
             }
         }
         if (!SKEW && interior) {  // _calc_implicit_part, diffusion.py:149-164
-            const int ks = ksv[q];
-            const double del = (k < nz - 1) ? mul(dt_dzw[k], k33) : 0.0;
-            const double delm = (k > 0) ? mul(dt_dzw[k - 1], k33m) : 0.0;
-            double b;
+            const int ks = b.ksv[q];
+            const double del = (k < nz - 1) ? mul(lv.dt_dzw[k], k33) : 0.0;
+            const double delm = (k > 0) ? mul(lv.dt_dzw[k - 1], k33m) : 0.0;
+            double diag;
             if (k == ks)
-                b = add(1.0, strict::div(del, ddzt[k]));  // b_tri_edge
+                diag = add(1.0, strict::div(del, lv.ddzt[k]));  // b_tri_edge
             else if (k == nz - 1)
-                b = add(1.0, strict::div(delm, ddzt[k]));
+                diag = add(1.0, strict::div(delm, lv.ddzt[k]));
             else
-                b = add(1.0, strict::div(add(del, delm), ddzt[k]));
-            D[s] = b;
-            U[s] = (k < nz - 1) ? strict::div(-del, ddzt[k]) : 0.0;
-            if (k > 0) L[s - 1] = (k > ks) ? strict::div(-delm, ddzt[k]) : 0.0;
+                diag = add(1.0, strict::div(add(del, delm), lv.ddzt[k]));
+            b.D[s] = diag;
+            b.U[s] = (k < nz - 1) ? strict::div(-del, lv.ddzt[k]) : 0.0;
+            if (k > 0) b.L[s - 1] = (k > ks) ? strict::div(-delm, lv.ddzt[k]) : 0.0;
         }
     }
-    __syncthreads();  // also orders this CTA's diss[] stores before the phase D loads of its own cells
+}
 
-    // ---- phase C: one thread per water column, dgtsv on all right-hand sides ----------------------
-    if (!SKEW) {
-        if (i_int) {
-            for (int q = threadIdx.x; q < ncols; q += kUpdBlock) {
-                const int j = j0 + q;
-                const int ks = ksv[q];
-                if (j >= 2 && j < M - 2 && ks >= 0) {
-                    const int o = q * pitch;
-                    dgtsv_column<NTR>(ks, nz, 1, L + o, D + o, U + o, R[0] + o, R[NTR - 1] + o);
-                }
-            }
+// phase C: one thread per water column, dgtsv on all right-hand sides
+template <int NTR>
+__device__ __forceinline__ void phase_c(const UpdConst& u, const TileBuf& b, const TileGeom& g, int tid, int nthr) {
+    if (!g.i_int) return;
+    for (int q = tid; q < g.ncols; q += nthr) {
+        const int j = g.j0 + q;
+        const int ks = b.ksv[q];
+        if (j >= 2 && j < u.M - 2 && ks >= 0) {
+            const int o = q * u.pitch;
+            dgtsv_column<NTR>(ks, u.nz, 1, b.L + o, b.D + o, b.U + o, b.R[0] + o, b.R[NTR - 1] + o);
         }
-        __syncthreads();
     }
+}
 
+// phase D: implicit result, tendency, dissipation on the W grid
+template <int NTR, bool SKEW, bool ENERGY>
+__device__ __forceinline__ void phase_d(const DiffArgs& a, const Scratch& f, const UpdConst& u, const LevelTabs& lv,
+                                        const TileBuf& b, const TileGeom& g, int tid, int nthr) {
+    const int M = u.M, nz = u.nz, pitch = u.pitch, tau = u.tau, taup1 = u.taup1;
+    const double gr = u.gr;
+    const Divisor ddt = u.ddt;
     // ---- phase D ----------------------------------------------------------------------------------
-    for (int idx = threadIdx.x; idx < ncells; idx += kUpdBlock) {
+    for (int idx = tid; idx < g.ncells; idx += nthr) {
         const int q = idx / nz, k = idx - q * nz;
-        const int j = j0 + q;
-        const size_t c = base + idx;
+        const int j = g.j0 + q;
+        const size_t c = g.base + idx;
         const int s = q * pitch + k;
-        const bool interior = i_int && j >= 2 && j < M - 2;
-        const int ks = ksv[q];
+        const bool interior = g.i_int && j >= 2 && j < M - 2;
+        const int ks = b.ksv[q];
         const bool land = ks >= 0;
         const bool up = k < nz - 1;
         const bool solved = !SKEW && interior && land && k >= ks;
@@ -347,7 +383,7 @@ update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch
 #pragma unroll
         for (int t = 0; t < NTR; ++t) {
             if (solved) {  // where(water_mask, sol, tr); diffusion.py:168,203-204
-                const double nw = R[t][s];
+                const double nw = b.R[t][s];
                 a.t[t].dtracer[c] = add(dtr_mid[t], strict::div(sub(nw, old[t]), ddt));
                 a.t[t].tr[c * 3 + taup1] = nw;
             }
@@ -357,21 +393,21 @@ update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch
                 if (up) {
                     const double m = mul(0.5, add(d0[t], d1[t]));
                     const double edge = (land && k == ks) ? 1.0 : 0.0, water = (land && k > ks) ? 1.0 : 0.0;
-                    const double dzw_pad = ddzw[k > 0 ? k - 1 : 0].y;
-                    dw = add(mul(add(m, mul(0.5, strict::div(mul(d0[t], dzw_pad), ddzw[k]))), edge), mul(m, water));
+                    const double dzw_pad = lv.ddzw[k > 0 ? k - 1 : 0].y;
+                    dw = add(mul(add(m, mul(0.5, strict::div(mul(d0[t], dzw_pad), lv.ddzw[k]))), edge), mul(m, water));
                 } else {
                     dw = mul(d0[t], land ? 1.0 : 0.0);
                 }
                 P = add(P, dw);  // diffusion.py:246-249
                 if (interior && up) {  // diffusion.py:254-279
-                    const double fxa = strict::div(add(-x1[t], x0[t]), ddzw[k]);
+                    const double fxa = strict::div(add(-x1[t], x0[t]), lv.ddzw[k]);
                     double v;
                     if (SKEW) {
                         v = mul(mul(mul(gr, fxa), ftc[t]), mW);
                     } else {
                         // tr[taup1] after the update: R holds it for every interior cell of the tile
-                        const double dtr = sub(R[t][s + 1], R[t][s]);
-                        v = mul(mul(gr, fxa), add(mul(ftc[t], mW), mul(strict::div(mul(k33, dtr), ddzw[k]), mW)));
+                        const double dtr = sub(b.R[t][s + 1], b.R[t][s]);
+                        v = mul(mul(gr, fxa), add(mul(ftc[t], mW), mul(strict::div(mul(k33, dtr), lv.ddzw[k]), mW)));
                     }
                     P = add(P, v);
                 }
@@ -381,23 +417,73 @@ update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch
     }
 }
 
+__device__ __forceinline__ UpdConst upd_const(const DiffArgs& a, int pitch, double fac_diss, double gr) {
+    UpdConst u;
+    u.N = a.g.N;
+    u.M = a.g.M;
+    u.nz = a.g.nz;
+    u.pitch = pitch;
+    u.tau = *a.tau;
+    u.taup1 = *a.taup1;
+    u.plane = (size_t)a.g.M * a.g.nz;
+    u.dt = a.dt_tracer;
+    u.fac_diss = fac_diss;
+    u.gr = gr;
+    u.ddt = make_divisor(a.dt_tracer);
+    return u;
+}
+
+// ---- one tile per CTA, phases separated by CTA barriers --------------------------------------------------
+// (A persistent, warp-specialised variant -- warp 0 solving tile n while warps 1-3 stream tiles n+1 and
+// n-1 through a second shared-memory buffer, named barriers FULL/DONE -- was built on these same phase
+// functions, verified bit-identical and measured 8-10 % SLOWER on both benchmark grids: with the tile
+// double buffered only half as many columns are being solved per SM, and 12 streaming warps per SM move
+// less data than the 24 of this kernel.  DESIGN.md section 3.2.)
+template <int NTR, bool SKEW, bool ENERGY>
+__global__ void __launch_bounds__(kUpdBlock, 6)
+update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch, const double fac_diss,
+              const double gr) {
+    extern __shared__ double sm[];
+    const int N = a.g.N, nz = a.g.nz;
+    const int i = 1 + blockIdx.y;
+    if ((i == 1 && a.skip_west_ring) || (i == N - 2 && a.skip_east_ring)) return;  // a neighbouring sub-slab's interior
+    const UpdConst u = upd_const(a, pitch, fac_diss, gr);
+    LevelTabs lv;
+    lv.ddzt = reinterpret_cast<Divisor*>(sm);
+    lv.ddzw = lv.ddzt + nz;
+    lv.dt_dzw = reinterpret_cast<double*>(lv.ddzw + nz);
+    const TileBuf b = tile_buf_at(lv.dt_dzw + nz, cols, pitch, NTR);
+    const TileGeom g = tile_geom(u, i, 1 + blockIdx.x * cols, cols);
+    fill_level_tabs(a, lv, nz, u.dt, threadIdx.x, kUpdBlock);
+    fill_tile_tabs(a, u, b, g, threadIdx.x, kUpdBlock);
+    __syncthreads();
+    phase_b<NTR, SKEW, ENERGY>(a, f, u, lv, b, g, threadIdx.x, kUpdBlock);
+    __syncthreads();  // also orders this CTA's diss[] stores before the phase D loads of its own cells
+    if (!SKEW) {
+        phase_c<NTR>(u, b, g, threadIdx.x, kUpdBlock);
+        __syncthreads();
+    }
+    phase_d<NTR, SKEW, ENERGY>(a, f, u, lv, b, g, threadIdx.x, kUpdBlock);
+}
+
 template <int NTR, bool SKEW, bool ENERGY>
 void launch_update(cudaStream_t s, const DiffArgs& a, const Scratch& f) {
     const int M = a.g.M, N = a.g.N, nz = a.g.nz;
     const int pitch = nz | 1;
-    const int narr = SKEW ? 0 : 3 + NTR;
+    const double fac_diss = 0.5 * a.grav / a.rho_0;  // diffusion.py (core) :19-21, Python float arithmetic
+    const double gr = -a.grav / a.rho_0;             // isoneutral/diffusion.py:259,268
     int cols = max(1, 640 / nz);
     if (const char* e = getenv("VEROS_B200_UPD_CELLS")) cols = max(1, atoi(e) / nz);  // tuning knob (tile cells)
     cols = min(cols, M - 2);
+    const size_t lev_bytes = (size_t)nz * (2 * sizeof(Divisor) + 8);
+    const int tiles_per_row = (M - 2 + cols - 1) / cols;
     const int want_tiles = 4 * 148;  // small grids: spread over the SMs
     const int rows = N - 2;
-    if (((M - 2 + cols - 1) / cols) * rows < want_tiles) {
+    if (tiles_per_row * rows < want_tiles) {
         const int per_row = (want_tiles + rows - 1) / rows;
         cols = max(1, (M - 2 + per_row - 1) / per_row);
     }
-    const size_t smem = (size_t)(3 + NTR) * 8 * cols * pitch + (size_t)nz * (2 * sizeof(Divisor) + 8) +
-                        (size_t)cols * (2 * sizeof(Divisor) + sizeof(int)) + 16;
-    (void)narr;
+    const size_t smem = lev_bytes + 8 * ((size_t)(3 + NTR) * cols * pitch + (size_t)cols * 4 + (cols + 1) / 2 + 1) + 16;
     auto kern = update_kernel<NTR, SKEW, ENERGY>;
     static bool configured = false;
     if (!configured) {
@@ -405,8 +491,6 @@ void launch_update(cudaStream_t s, const DiffArgs& a, const Scratch& f) {
         configured = true;
     }
     dim3 grid((M - 2 + cols - 1) / cols, N - 2);
-    const double fac_diss = 0.5 * a.grav / a.rho_0;  // diffusion.py (core) :19-21, Python float arithmetic
-    const double gr = -a.grav / a.rho_0;             // isoneutral/diffusion.py:259,268
     kern<<<grid, kUpdBlock, smem, s>>>(a, f, cols, pitch, fac_diss, gr);
     count_launch();
     check_launch("update_kernel");
