@@ -55,6 +55,9 @@ def stalls(rep, regex, thr=0.02):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{regex}"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
+    if len(rows) < 3:
+        print(f"no kernel matching {regex!r} in {rep}")
+        return
     hdr = rows[1]
     data = [r for r in rows[2:] if len(r) == len(hdr) and r[0] != "Address"]
 
