@@ -221,6 +221,14 @@ iso_pre_kernel(const PreArgs a) {
         const bool hasKm = k >= 1, hasKp = k < nz - 1;
         const int km = hasKm ? -1 : 0, kp = hasKp ? 1 : 0;  // clamped neighbours (pad_z_edges)
         const size_t ce = c + plane, cn = c + nz, cw = c - plane, cs = c - nz;
+        // At k = 0 the kr = 0 entries of Ai_ez / Ai_nz keep their old values and the fluxes read them
+        // (times a zero difference).  They are cold DRAM lines: fetch them before anything else, not
+        // next to their use behind the stores to the same array, where nothing could hide the miss.
+        double Aez_old[2] = {0.0, 0.0}, Anz_old[2] = {0.0, 0.0};
+        if (FLUX && !hasKm) {
+            if (inE) { Aez_old[0] = a.Ai_ez[c * 4]; Aez_old[1] = a.Ai_ez[c * 4 + 2]; }
+            if (inN) { Anz_old[0] = a.Ai_nz[c * 4]; Anz_old[1] = a.Ai_nz[c * 4 + 2]; }
+        }
         // metric table entries of this level / row / plane (read-only path, L1 resident)
         struct { Divisor d4zt; double rdzw, dzw, pabs; } L1, L0;
         {
@@ -328,7 +336,7 @@ iso_pre_kernel(const PreArgs a) {
             a.K_11[c] = K11;
             if (FLUX) {
                 // at k = 0 the kr = 0 entries of Ai_ez keep their old values; they multiply a zero difference
-                const double A00 = hasKm ? A[0][0] : out[0], A10 = hasKm ? A[1][0] : out[2];
+                const double A00 = hasKm ? A[0][0] : Aez_old[0], A10 = hasKm ? A[1][0] : Aez_old[1];
                 fl[0][0] = flux_face(diffloc, A00, A[0][1], A10, A[1][1], dT0c, dT1c, dT0e, dT1e, dTxc, L1.d4zt, Rj.cdxu, K11);
                 fl[1][0] = flux_face(diffloc, A00, A[0][1], A10, A[1][1], dS0c, dS1c, dS0e, dS1e, dSxc, L1.d4zt, Rj.cdxu, K11);
             }
@@ -392,7 +400,7 @@ iso_pre_kernel(const PreArgs a) {
             const double K22 = sumz * rdzt4;
             a.K_22[c] = K22;
             if (FLUX) {
-                const double A00 = hasKm ? A[0][0] : out[0], A10 = hasKm ? A[1][0] : out[2];
+                const double A00 = hasKm ? A[0][0] : Anz_old[0], A10 = hasKm ? A[1][0] : Anz_old[1];
                 fl[0][1] = strict::mul(Rj.cosu, flux_face(diffloc, A00, A[0][1], A10, A[1][1], dT0c, dT1c, dT0n, dT1n,
                                                           dTyc, L1.d4zt, Rj.dyu, K22));
                 fl[1][1] = strict::mul(Rj.cosu, flux_face(diffloc, A00, A[0][1], A10, A[1][1], dS0c, dS1c, dS0n, dS1n,
