@@ -158,6 +158,9 @@ def main():
     ap.add_argument("--replicas", type=int, default=0, help="state replicas rotated through (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the global_1deg side measurement")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (forced above 20 M cells per rank)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank gets a slab of the named size; strong: the named grid is split over the ranks")
     ap.add_argument("--profile", action="store_true",
                     help="only warm-up + timed steps + per-kernel pass (for ncu launch lists): no e2e, cpu or extra legs")
     ap.add_argument("--overlap", default="auto", choices=["auto", "on", "off"],
@@ -206,6 +209,10 @@ def main():
     name, kw = workload_kwargs(args, world)
     if world > 1 and name != "bench_1M":
         nxl = synthetic.WORKLOADS[name]["nx"]
+        if args.scaling == "strong":
+            if nxl % world:
+                raise SystemExit(f"--scaling strong: nx = {nxl} is not divisible by {world} ranks")
+            nxl //= world
         kw = dict(nx=nxl, x_offset=rank * nxl, nx_global=nxl * world)
     elif world > 1:
         kw = dict(seed=17 + rank)
@@ -219,6 +226,8 @@ def main():
     probe = IsoState.from_numpy(st, dev)
     state_bytes = sum(t.numel() * t.element_size() for t in vars(probe.variables).values() if hasattr(t, 'numel'))
     replicas = args.replicas or max(2, min(8, int(3 * L2_BYTES / state_bytes) + 1))
+    if state_bytes > 4e9 and not args.replicas:
+        replicas = 1  # one pass over the state already streams several L2 sizes
     states = [probe] + [IsoState.from_numpy(st, dev) for _ in range(replicas - 1)]
 
     plans = [isoneutral.StepPlan(s) for s in states]  # argument marshalling done once, as under XLA
@@ -333,19 +342,23 @@ def main():
     # ---- end to end: host buffers in, host buffers out ----------------------------------------------
     del states[1:]
     torch.cuda.empty_cache()
-    hs = HostStepper(st, dev)
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        hs.step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        hs.step()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    clocks = sampler.stop() if rank == 0 else None  # sampled from warm-up to here (all under load)
-    e2e = {"value": world * cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes,
-           "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps}
+    if args.no_e2e or cells > 20_000_000:
+        clocks = sampler.stop() if rank == 0 else None
+        e2e = None  # the pinned staging buffers of this leg would be tens of GB
+    else:
+        hs = HostStepper(st, dev)
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            hs.step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            hs.step()
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        clocks = sampler.stop() if rank == 0 else None  # sampled from warm-up to here (all under load)
+        e2e = {"value": world * cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes,
+               "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps}
 
     extra = None
     if rank == 0 and world == 1 and not args.no_extra and name != "global_1deg":
@@ -378,16 +391,17 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": name, "nx": nx, "ny": ny, "nz": nz, "cells_per_gpu": cells,
                 "eq_of_state_type": int(st["eq_of_state_type"]), "enable_conserve_energy": energy,
                 "parallelism": f"x-slabs x{world}" + ((" + NCCL ring halo exchange of temp/salt[taup1]" +
                                 (", boundary strips first, exchange overlapped with interior" if overlap else ", exchange after the step"))
                                 if world > 1 else ""),
-                "l2": f"inputs larger than L2: {replicas} state replicas of {state_bytes / 1e6:.0f} MB rotated, "
-                      f"no replica is touched twice in a row",
+                "l2": (f"inputs larger than L2: {replicas} state replicas of {state_bytes / 1e6:.0f} MB rotated, "
+                       f"no replica is touched twice in a row") if replicas > 1 else
+                      f"inputs larger than L2: one state of {state_bytes / 1e6:.0f} MB streamed per step",
             },
             "roofline": roofline, "step_roofline": step_roofline, "cpu_baseline": base, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
