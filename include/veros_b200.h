@@ -86,6 +86,15 @@ typedef struct VerosB200IsoDescriptor {
     double rho_0;
 } VerosB200IsoDescriptor;
 
+/* vertmix_tempsalt: sizes and the tracer time step. */
+typedef struct VerosB200VmixDescriptor {
+    int32_t nx_tot; /* N = nx + 4 */
+    int32_t ny_tot; /* M = ny + 4 */
+    int32_t nz;
+    int32_t flags; /* reserved, 0 */
+    double dt_tracer;
+} VerosB200VmixDescriptor;
+
 /* ------------------------------------------------------------------------------ compute ops */
 
 /* Column solve on the model's native (X,Y,nz) z-contiguous layout, replacing
@@ -140,6 +149,17 @@ void veros_b200_iso_diffusion_f64(void* stream, void** buffers, const char* opaq
  * (results): 31..42 = operands 0..11, 43 workspace (veros_b200_iso_step_workspace_bytes) */
 void veros_b200_iso_step_f64(void* stream, void** buffers, const char* opaque, size_t opaque_len);
 
+/* The step right after the isoneutral path: vertmix_tempsalt,
+ * veros/core/thermodynamics.py:248-288 -- coefficient assembly from kappaH, the two solve_implicit calls
+ * (one dgtsv factorisation shared by both tracers) and the dtemp_vmix / dsalt_vmix tendencies in one
+ * kernel; bit-identical to the reference's NumPy backend.  The enforce_boundaries calls that follow in
+ * the reference (:290-297) are the caller's halo exchange (veros_b200_halo_pack_unpack + NCCL).
+ * opaque: VerosB200VmixDescriptor.
+ * buffers (operands): 0 temp, 1 salt (N,M,nz,3), 2 taup1 (int32[1]), 3 kappaH (N,M,nz),
+ *          4 forc_temp_surface, 5 forc_salt_surface (N,M), 6 kbot (int32 N,M), 7 dzt, 8 dzw (nz)
+ * (results): 9 temp, 10 salt, 11 dtemp_vmix, 12 dsalt_vmix (N,M,nz; every element written) */
+void veros_b200_vertmix_tempsalt_f64(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
 /* ------------------------------------------------------------------------ host-side helpers */
 
 /* Scratch the caller must provide as the last result (0 is possible; then pass any valid pointer). */
@@ -169,7 +189,7 @@ void veros_b200_halo_pack_unpack(void* stream, int mode, void** fields, int nfie
 void veros_b200_profile_events(void** events, int n);
 
 int veros_b200_abi_version(void);
-/* sizeof() of descriptor 0 = Tridiag, 1 = Solve, 2 = Iso as compiled into the library. */
+/* sizeof() of descriptor 0 = Tridiag, 1 = Solve, 2 = Iso, 3 = Vmix as compiled into the library. */
 size_t veros_b200_descriptor_size(int which);
 /* Number of kernel launches enqueued by this library since load (bench.py's gpu_launches). */
 unsigned long long veros_b200_launch_count(void);

@@ -21,6 +21,9 @@
  *   veros/core/operators.py:60-77                solve_tridiagonal_numpy (LAPACK dgtsv)
  *   veros/core/operators.py:133-156, special/tdma_cython_.pyx:8-25   Thomas cp/dp recurrence
  *   veros/core/diffusion.py:9-62                 compute_dissipation, dissipation_on_wgrid
+ *   veros/core/thermodynamics.py:248-300         vertmix_tempsalt (golden vectors
+ *                                                tests/golden/vmix_*.npz, bit-for-bit)
+ *   veros/core/utilities.py:8-20                 enforce_boundaries
  *   veros/core/density/{linear_eq,nonlinear_eq1,nonlinear_eq2,nonlinear_eq3,gsw}.py, get_rho.py:93-131
  *
  * Layout: C order, z fastest: f[i][j][k] -> (i*M + j)*nz + k ; tracers (N,M,nz,3) time level last;
@@ -589,4 +592,64 @@ void oracle_iso_diffusion(const oracle_params *P, int32_t iso, double *tr, doubl
 #undef X
         free(diss);
     }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * vertmix_tempsalt (veros/core/thermodynamics.py:248-300): implicit vertical mixing of T and S with
+ * kappaH and the surface fluxes, tendencies dtemp_vmix / dsalt_vmix, then enforce_boundaries
+ * (utilities.py:8-20) on temp/salt[..., taup1].  temp, salt: (N,M,nz,3); kappaH: (N,M,nz);
+ * forc_*_surface: (N,M); dtemp_vmix, dsalt_vmix: (N,M,nz) outputs (every element written).
+ * ---------------------------------------------------------------------------------------- */
+void oracle_vertmix_tempsalt(int32_t N, int32_t M, int32_t nz, int32_t taup1, int32_t cyclic_x, double dt,
+                             double *temp, double *salt, const double *kappaH, const double *forc_temp,
+                             const double *forc_salt, const int32_t *kbot, const double *dzt, const double *dzw,
+                             double *dtemp_vmix, double *dsalt_vmix, int32_t tdma_mode) {
+    const size_t n3 = (size_t)N * M * nz;
+    double *trs[2] = {temp, salt};
+    double *dtrs[2] = {dtemp_vmix, dsalt_vmix};
+    const double *forc[2] = {forc_temp, forc_salt};
+    for (int t = 0; t < 2; t++) /* :256-257 */
+        for (size_t c = 0; c < n3; c++) dtrs[t][c] = trs[t][c * 3 + taup1];
+#pragma omp parallel
+    {
+    double *a = calloc(nz, 8), *b = calloc(nz, 8), *c = calloc(nz, 8), *d = calloc(nz, 8), *delta = calloc(nz, 8);
+    double *x = calloc(nz, 8), *w1 = calloc(nz, 8), *w2 = calloc(nz, 8);
+    uint8_t *water = calloc(nz, 1), *edge = calloc(nz, 1);
+#pragma omp for schedule(static)
+    for (int i = 2; i < N - 2; i++)
+        for (int j = 2; j < M - 2; j++) {
+            int ks = kbot[i * M + j] - 1;
+            int land = ks >= 0;
+            for (int k = 0; k < nz; k++) {
+                water[k] = land && k >= ks;
+                edge[k] = land && k == ks;
+                delta[k] = (k < nz - 1) ? dt / dzw[k] * kappaH[IDX(i, j, k)] : 0.0; /* :267-270 */
+            }
+            for (int k = 0; k < nz; k++) {
+                a[k] = (k >= 1) ? -delta[k - 1] / dzt[k] : 0.0;                     /* :271 */
+                b[k] = (k >= 1) ? 1 + (delta[k] + delta[k - 1]) / dzt[k] : 0.0;     /* :272 */
+                c[k] = (k < nz - 1) ? -delta[k] / dzt[k] : 0.0;                     /* :274 */
+                if (edge[k]) b[k] = 1 + delta[k] / dzt[k];                          /* :273, b_edge */
+            }
+            for (int t = 0; t < 2; t++) {
+                double *tr = trs[t];
+                for (int k = 0; k < nz; k++) d[k] = tr[TIDX(i, j, k, taup1)];
+                d[nz - 1] = d[nz - 1] + dt * forc[t][i * M + j] / dzt[nz - 1];      /* :276, :282 */
+                solve_column(nz, a, b, c, d, water, edge, x, w1, w2, tdma_mode);
+                for (int k = 0; k < nz; k++)
+                    if (water[k]) tr[TIDX(i, j, k, taup1)] = x[k];                  /* :279, :285 */
+            }
+        }
+    free(a); free(b); free(c); free(d); free(delta); free(x); free(w1); free(w2); free(water); free(edge);
+    }
+    for (int t = 0; t < 2; t++) /* :287-288 */
+        for (size_t c = 0; c < n3; c++) dtrs[t][c] = (trs[t][c * 3 + taup1] - dtrs[t][c]) / dt;
+    if (cyclic_x) /* enforce_boundaries: [-2:] <- [2:4], [:2] <- [-4:-2] */
+        for (int t = 0; t < 2; t++)
+            for (int g = 0; g < 2; g++)
+                for (int j = 0; j < M; j++)
+                    for (int k = 0; k < nz; k++) {
+                        trs[t][TIDX(N - 2 + g, j, k, taup1)] = trs[t][TIDX(2 + g, j, k, taup1)];
+                        trs[t][TIDX(g, j, k, taup1)] = trs[t][TIDX(N - 4 + g, j, k, taup1)];
+                    }
 }

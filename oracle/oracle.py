@@ -132,6 +132,24 @@ def isoneutral_step(st, tdma_mode=0):
     return st
 
 
+def vertmix_tempsalt(st, tdma_mode=0):
+    """veros/core/thermodynamics.py:248-300 in place on st["temp"|"salt"] (time level taup1); creates
+    st["dtemp_vmix"|"dsalt_vmix"].  Includes the single-process enforce_boundaries of :290-297."""
+    N, M, nz = st["kappaH"].shape
+    st["temp"] = _f64(st["temp"]).copy()
+    st["salt"] = _f64(st["salt"]).copy()
+    st["dtemp_vmix"] = np.zeros((N, M, nz))
+    st["dsalt_vmix"] = np.zeros((N, M, nz))
+    args = [st["temp"], st["salt"], _f64(st["kappaH"]), _f64(st["forc_temp_surface"]), _f64(st["forc_salt_surface"]),
+            np.ascontiguousarray(st["kbot"], dtype=np.int32), _f64(st["dzt"]), _f64(st["dzw"]),
+            st["dtemp_vmix"], st["dsalt_vmix"]]
+    lib().oracle_vertmix_tempsalt(
+        ctypes.c_int32(N), ctypes.c_int32(M), ctypes.c_int32(nz), ctypes.c_int32(int(st["taup1"])),
+        ctypes.c_int32(int(bool(st.get("enable_cyclic_x", False)))), ctypes.c_double(float(st["dt_tracer"])),
+        *[_p(a) for a in args], ctypes.c_int32(tdma_mode))
+    return st
+
+
 def solve_implicit(a, b, c, d, water_mask, edge_mask, b_edge=None, d_edge=None, mode=0):
     """mode 0: dgtsv (no-pivot) operation order; mode 1: Thomas cp/dp recurrence."""
     a, b, c, d = map(_f64, (a, b, c, d))

@@ -11,7 +11,8 @@ KS = ("K_11", "K_22", "K_33")
 
 
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    names = (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return sorted(n for n in names if not n.startswith("vmix_"))
 
 
 def load_golden(name):
@@ -30,6 +31,21 @@ def load_golden(name):
         if k not in st:
             st[k] = np.zeros(st["K_iso"].shape + (2, 2))
     return st, stages
+
+
+def vmix_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("vmix_") and f.endswith(".npz"))
+
+
+def load_vmix_golden(name):
+    """(inputs keyed by reference names, outputs) of a vertmix_tempsalt fixture (make_golden_vmix.py)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    st, out = {}, {}
+    for key in z.files:
+        group, var = key.split("__", 1)
+        val = z[key] if z[key].ndim else z[key].item()
+        (out if group == "out" else st)[var] = val
+    return st, out
 
 
 def copy_state(st):

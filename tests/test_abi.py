@@ -49,6 +49,7 @@ def test_descriptor_layouts(lib):
     assert lib.veros_b200_descriptor_size(0) == ctypes.sizeof(_lib.TridiagDescriptor) == 8  # reference: 2 ints
     assert lib.veros_b200_descriptor_size(1) == ctypes.sizeof(_lib.SolveDescriptor) == 16
     assert lib.veros_b200_descriptor_size(2) == ctypes.sizeof(_lib.IsoDescriptor) == 72
+    assert lib.veros_b200_descriptor_size(3) == ctypes.sizeof(_lib.VmixDescriptor) == 24
     assert lib.veros_b200_abi_version() == _lib.ABI_VERSION
 
 

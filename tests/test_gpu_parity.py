@@ -13,6 +13,7 @@ Tolerances (BASELINE.json north_star: 1e-12 relative on diffusivities and tracer
 import numpy as np
 import pytest
 
+import helpers
 from helpers import AI, KS, copy_state, golden_names, load_golden, norm_err, tendency_err
 
 torch = pytest.importorskip("torch")
@@ -472,3 +473,63 @@ def test_tracer_halo_exchange_kernel_matches_torch_path(dev):
     decomp.exchange_halos_x(c, cyclic=True)
     decomp.TracerHaloExchange(d, cyclic=True)()
     assert torch.equal(c[0], d[0])
+
+
+# ------------------------------------------------------------------ vertmix_tempsalt
+@pytest.mark.parametrize("name", helpers.vmix_golden_names())
+def test_vertmix_tempsalt_bitexact_vs_reference_golden(name, dev):
+    """veros/core/thermodynamics.py:248-300 including enforce_boundaries: bit for bit against the
+    reference's NumPy backend (random kappaH makes dgtsv interchange rows in many columns)."""
+    from veros_b200 import thermodynamics
+    from veros_b200.state import IsoState
+
+    st, out = helpers.load_vmix_golden(name)
+    gs = IsoState.from_numpy(st, dev, strict=False)
+    res = thermodynamics.vertmix_tempsalt(gs)
+    assert res._fields == ("dtemp_vmix", "temp", "dsalt_vmix", "salt")  # KernelOutput order of :299
+    gs.variables.update(res)
+    got = gs.to_numpy(["temp", "salt", "dtemp_vmix", "dsalt_vmix"])
+    for k, v in got.items():
+        assert np.array_equal(v, out[k]), k
+
+
+@pytest.mark.parametrize("shape,cyclic", [((48, 40, 50), False), ((24, 40, 115), True), ((7, 5, 1), True), ((300, 9, 2), False)])
+def test_vertmix_tempsalt_vs_oracle(shape, cyclic, dev):
+    from oracle import oracle
+    from veros_b200 import synthetic, thermodynamics
+    from veros_b200.state import IsoState
+
+    nx, ny, nz = shape
+    base = synthetic.make_workload("bench_1M", nx=nx, ny=ny, nz=max(nz, 2), enable_cyclic_x=cyclic)
+    rng = np.random.default_rng(5)
+    N, M = nx + 4, ny + 4
+    st = {k: base[k] for k in ("kbot", "taup1", "dt_tracer")}
+    st["enable_cyclic_x"] = cyclic
+    st["temp"] = np.ascontiguousarray(base["temp"][:, :, :nz])
+    st["salt"] = np.ascontiguousarray(base["salt"][:, :, :nz])
+    st["kbot"] = np.minimum(base["kbot"], nz).astype(np.int32)
+    st["dzt"], st["dzw"] = base["dzt"][:nz].copy(), base["dzw"][:nz].copy()
+    st["kappaH"] = np.abs(rng.standard_normal((N, M, nz))) * 1e-3
+    st["forc_temp_surface"] = rng.standard_normal((N, M)) * 1e-5
+    st["forc_salt_surface"] = rng.standard_normal((N, M)) * 1e-6
+    ref = oracle.vertmix_tempsalt(copy_state(st))
+    gs = IsoState.from_numpy(st, dev, strict=False)
+    gs.variables.update(thermodynamics.vertmix_tempsalt(gs))
+    got = gs.to_numpy(["temp", "salt", "dtemp_vmix", "dsalt_vmix"])
+    for k, v in got.items():
+        assert np.array_equal(v, ref[k]), k
+    land = st["kbot"] == 0
+    assert np.array_equal(got["temp"][2:-2, 2:-2][land[2:-2, 2:-2]], st["temp"][2:-2, 2:-2][land[2:-2, 2:-2]])
+
+
+def test_vertmix_tempsalt_errors(dev):
+    from veros_b200 import _lib, thermodynamics
+    from veros_b200.state import IsoState
+
+    st, _ = helpers.load_vmix_golden(helpers.vmix_golden_names()[0])
+    gs = IsoState.from_numpy(st, dev, strict=False)
+    del gs.variables.kappaH
+    with pytest.raises(ValueError):
+        thermodynamics.vertmix_tempsalt(gs)
+    with pytest.raises(RuntimeError):  # truncated descriptor: the library latches an error instead of launching
+        _lib.call("veros_b200_vertmix_tempsalt_f64", [0] * 13, bytes(8), 0)

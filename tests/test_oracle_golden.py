@@ -3,6 +3,7 @@ NumPy implementation (tests/golden/make_golden.py).  CPU only."""
 import numpy as np
 import pytest
 
+import helpers
 from helpers import AI, KS, copy_state, golden_names, load_golden, norm_err
 from oracle import oracle
 
@@ -134,3 +135,14 @@ def test_random_systems_bitexact_vs_scipy_dgtsv():
     ref[water] = lapack.dgtsv(aa[water][1:], b[water], cc[water][:-1], d[water])[3]
     out = oracle.solve_tridiagonal(a, b, c, d, water, edge, mode=0)
     assert np.array_equal(out, ref)
+
+
+# ------------------------------------------------------------------ vertmix_tempsalt
+@pytest.mark.parametrize("name", helpers.vmix_golden_names())
+def test_oracle_vertmix_tempsalt_bitexact(name):
+    """veros/core/thermodynamics.py:248-300 incl. enforce_boundaries: bit for bit, also where dgtsv
+    interchanges rows (random kappaH is not positive)."""
+    st, out = helpers.load_vmix_golden(name)
+    got = oracle.vertmix_tempsalt(helpers.copy_state(st))
+    for k in ("temp", "salt", "dtemp_vmix", "dsalt_vmix"):
+        assert np.array_equal(got[k], out[k]), k

@@ -17,6 +17,7 @@ OPS = (
     "veros_b200_iso_pre_f64",
     "veros_b200_iso_diffusion_f64",
     "veros_b200_iso_step_f64",
+    "veros_b200_vertmix_tempsalt_f64",
 )
 HELPERS = (
     "veros_b200_iso_pre_workspace_bytes",
@@ -52,6 +53,11 @@ class IsoDescriptor(ctypes.Structure):
         ("K_iso_steep", ctypes.c_double), ("iso_slopec", ctypes.c_double), ("iso_dslope", ctypes.c_double),
         ("dt_tracer", ctypes.c_double), ("grav", ctypes.c_double), ("rho_0", ctypes.c_double),
     ]
+
+
+class VmixDescriptor(ctypes.Structure):
+    _fields_ = [("nx_tot", ctypes.c_int32), ("ny_tot", ctypes.c_int32), ("nz", ctypes.c_int32),
+                ("flags", ctypes.c_int32), ("dt_tracer", ctypes.c_double)]
 
 
 HAS_B_EDGE, HAS_D_EDGE = 1, 2
@@ -95,7 +101,7 @@ def lib():
     L.veros_b200_profile_events.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
     if L.veros_b200_abi_version() != ABI_VERSION:
         raise RuntimeError("libveros_b200.so ABI version mismatch; rebuild with `python -m veros_b200.build --force`")
-    for which, cls in enumerate((TridiagDescriptor, SolveDescriptor, IsoDescriptor)):
+    for which, cls in enumerate((TridiagDescriptor, SolveDescriptor, IsoDescriptor, VmixDescriptor)):
         if L.veros_b200_descriptor_size(which) != ctypes.sizeof(cls):
             raise RuntimeError(f"descriptor layout mismatch for {cls.__name__}")
     _lib = L

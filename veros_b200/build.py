@@ -22,6 +22,7 @@ SOURCES = {
     "iso_pre.cu": [],
     "iso_diffusion.cu": [],
     "halo.cu": [],
+    "vertmix.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -293,6 +293,35 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     prof_mark(s, 3);
 }
 
+void veros_b200_vertmix_tempsalt_f64(void* stream, void** B, const char* opaque, size_t len) {
+    const auto* d = unpack<VerosB200VmixDescriptor>(opaque, len, "vertmix_tempsalt: bad descriptor");
+    if (!d) return;
+    if (d->nx_tot < 0 || d->ny_tot < 0 || d->nz < 0 || !(d->dt_tracer > 0.0))
+        return set_error(VEROS_B200_ERR_BAD_ARGUMENT, "vertmix_tempsalt: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n3 = (size_t)d->nx_tot * d->ny_tot * d->nz;
+    if (n3 == 0) return;
+    alias_copy(s, B[9], B[0], n3 * 3 * 8);
+    alias_copy(s, B[10], B[1], n3 * 3 * 8);
+    VmixArgs a;
+    a.N = d->nx_tot;
+    a.M = d->ny_tot;
+    a.nz = d->nz;
+    a.temp = (double*)B[9];
+    a.salt = (double*)B[10];
+    a.taup1 = (const int32_t*)B[2];
+    a.kappaH = (const double*)B[3];
+    a.forc_temp = (const double*)B[4];
+    a.forc_salt = (const double*)B[5];
+    a.kbot = (const int32_t*)B[6];
+    a.dzt = (const double*)B[7];
+    a.dzw = (const double*)B[8];
+    a.dtemp_vmix = (double*)B[11];
+    a.dsalt_vmix = (double*)B[12];
+    a.dt_tracer = d->dt_tracer;
+    launch_vertmix(s, a);
+}
+
 void veros_b200_profile_events(void** events, int n) {
     g_prof_events = reinterpret_cast<cudaEvent_t*>(events);
     g_prof_n = events ? n : 0;
@@ -332,6 +361,7 @@ extern "C" size_t veros_b200_descriptor_size(int which) {
     case 0: return sizeof(VerosB200TridiagDescriptor);
     case 1: return sizeof(VerosB200SolveDescriptor);
     case 2: return sizeof(VerosB200IsoDescriptor);
+    case 3: return sizeof(VerosB200VmixDescriptor);
     default: return 0;
     }
 }

@@ -62,11 +62,24 @@ struct DiffArgs {
     double dt_tracer, grav, rho_0;
 };
 
+struct VmixArgs {  // vertmix_tempsalt, veros/core/thermodynamics.py:248-288
+    int N, M, nz;
+    double *temp, *salt;              // (N,M,nz,3) in/out (taup1 level)
+    const int32_t* taup1;
+    const double* kappaH;             // (N,M,nz)
+    const double *forc_temp, *forc_salt;  // (N,M)
+    const int32_t* kbot;
+    const double *dzt, *dzw;
+    double *dtemp_vmix, *dsalt_vmix;  // (N,M,nz) out
+    double dt_tracer;
+};
+
 // ---- launchers (one per translation unit) -----------------------------------------------------
 void launch_iso_pre(cudaStream_t s, const PreArgs& a, bool profile = false);
 void prof_mark(cudaStream_t s, int q);  // api.cu: records the q-th profiling event if a benchmark installed some
 size_t diffusion_workspace_doubles(int N, int M, int nz, int ntr);
 void launch_iso_diffusion_ws(cudaStream_t s, const DiffArgs& a, double* workspace);
+void launch_vertmix(cudaStream_t s, const VmixArgs& a);
 void launch_solve_implicit(cudaStream_t s, int ncol, int nz, const double* a, const double* b, const double* c,
                            const double* d, const uint8_t* water, const uint8_t* edge, const double* b_edge,
                            const double* d_edge, double* out);

@@ -16,7 +16,9 @@ from types import SimpleNamespace
 import numpy as np
 import torch
 
-F64_3D = ("K_iso", "K_gm", "K_11", "K_22", "K_33", "dtemp_iso", "dsalt_iso", "P_diss_iso", "P_diss_skew")
+F64_3D = ("K_iso", "K_gm", "K_11", "K_22", "K_33", "dtemp_iso", "dsalt_iso", "P_diss_iso", "P_diss_skew",
+          "kappaH", "dtemp_vmix", "dsalt_vmix")
+F64_2D = ("forc_temp_surface", "forc_salt_surface")
 F64_4D = ("temp", "salt", "int_drhodT", "int_drhodS")
 F64_5D = ("Ai_ez", "Ai_nz", "Ai_bx", "Ai_by")
 MASKS = ("maskT", "maskU", "maskV", "maskW")
@@ -25,7 +27,9 @@ METRICS_Y = ("dyt", "dyu", "cost", "cosu")
 METRICS_Z = ("dzt", "dzw", "zt")
 SETTINGS = ("eq_of_state_type", "enable_conserve_energy", "K_iso_steep", "iso_slopec", "iso_dslope",
             "dt_tracer", "grav", "rho_0")
-OPTIONAL = ("K_gm", "P_diss_skew", "int_drhodT", "int_drhodS", "P_diss_iso")
+OPTIONAL = ("K_gm", "P_diss_skew", "int_drhodT", "int_drhodS", "P_diss_iso",
+            # vertmix_tempsalt (veros_b200/thermodynamics.py)
+            "kappaH", "dtemp_vmix", "dsalt_vmix", "forc_temp_surface", "forc_salt_surface")
 
 
 def KernelOutput(**kwargs):
@@ -53,48 +57,57 @@ class IsoState:
 
     # ---- construction --------------------------------------------------------------------------
     @classmethod
-    def from_numpy(cls, st, device="cuda"):
-        """`st`: dict keyed by reference variable / setting names (see tests/helpers.py)."""
+    def from_numpy(cls, st, device="cuda", strict=True):
+        """`st`: dict keyed by reference variable / setting names (see tests/helpers.py).
+        strict=False accepts a state that only carries the variables of one of the neighbouring
+        kernels (e.g. vertmix_tempsalt); the op wrappers check for what they need."""
         device = torch.device(device)
-        N, M, nz = st["K_iso"].shape
+        N, M, nz = np.shape(st["temp"])[:3]
         vs = Variables()
 
         def put(name, arr, dtype):
             arr = np.ascontiguousarray(arr, dtype=dtype)
             setattr(vs, name, torch.from_numpy(arr).to(device))
 
-        for name in F64_3D + F64_4D + F64_5D + METRICS_X + METRICS_Y + METRICS_Z:
+        for name in F64_3D + F64_2D + F64_4D + F64_5D + METRICS_X + METRICS_Y + METRICS_Z:
             if name in st:
                 put(name, st[name], np.float64)
-            elif name not in OPTIONAL:
+            elif strict and name not in OPTIONAL:
                 raise KeyError(name)
         for name in MASKS:
-            put(name, np.asarray(st[name]).astype(np.uint8), np.uint8)
+            if name in st or strict:
+                put(name, np.asarray(st[name]).astype(np.uint8), np.uint8)
         put("kbot", st["kbot"], np.int32)
         for name in ("tau", "taup1"):
-            put(name, np.array([int(st[name])]), np.int32)
-            setattr(vs, name + "_host", int(st[name]))  # host copy for plumbing (halo packing)
-        settings = SimpleNamespace(**{k: st[k] for k in SETTINGS})
-        settings.eq_of_state_type = int(settings.eq_of_state_type)
-        settings.enable_conserve_energy = bool(settings.enable_conserve_energy)
+            if name in st or strict:
+                put(name, np.array([int(st[name])]), np.int32)
+                setattr(vs, name + "_host", int(st[name]))  # host copy for plumbing (halo packing)
+        settings = SimpleNamespace(**{k: st[k] for k in SETTINGS if strict or k in st})
+        if hasattr(settings, "eq_of_state_type"):
+            settings.eq_of_state_type = int(settings.eq_of_state_type)
+        if hasattr(settings, "enable_conserve_energy"):
+            settings.enable_conserve_energy = bool(settings.enable_conserve_energy)
         for k in SETTINGS[2:]:
-            setattr(settings, k, float(getattr(settings, k)))
+            if hasattr(settings, k):
+                setattr(settings, k, float(getattr(settings, k)))
+        settings.enable_cyclic_x = bool(st.get("enable_cyclic_x", False))
         settings.nx, settings.ny, settings.nz = N - 4, M - 4, nz
         obj = cls(vs, settings, device)
-        obj.validate()
+        obj.validate(strict)
         return obj
 
-    def validate(self):
+    def validate(self, strict=True):
         vs, st = self.variables, self.settings
         N, M, nz = st.nx + 4, st.ny + 4, st.nz
         shapes = {**{n: (N, M, nz) for n in F64_3D + MASKS}, **{n: (N, M, nz, 3) for n in F64_4D},
+                  **{n: (N, M) for n in F64_2D},
                   **{n: (N, M, nz, 2, 2) for n in F64_5D}, **{n: (N,) for n in METRICS_X},
                   **{n: (M,) for n in METRICS_Y}, **{n: (nz,) for n in METRICS_Z}, "kbot": (N, M),
                   "tau": (1,), "taup1": (1,)}
         for name, shape in shapes.items():
             t = getattr(vs, name, None)
             if t is None:
-                if name in OPTIONAL:
+                if name in OPTIONAL or not strict:
                     continue
                 raise ValueError(f"state is missing variable {name}")
             if tuple(t.shape) != shape:
@@ -104,6 +117,8 @@ class IsoState:
                 raise TypeError(f"{name} has dtype {t.dtype}, expected {want}")
             if not t.is_contiguous():
                 raise ValueError(f"{name} must be C-contiguous")
+        if not strict:
+            return
         if st.enable_conserve_energy:
             for name in ("int_drhodT", "int_drhodS", "P_diss_iso"):
                 if getattr(vs, name, None) is None:

@@ -1,0 +1,41 @@
+"""The step right after the isoneutral path: ``vertmix_tempsalt`` (veros/core/thermodynamics.py:248-300).
+
+Same name, argument and return convention as the reference kernel:
+
+    vs.update(thermodynamics.vertmix_tempsalt(state))
+
+One launch of ``veros_b200_vertmix_tempsalt_f64`` (csrc/vertmix.cu: coefficient assembly from kappaH,
+both column solves on one dgtsv factorisation, the dtemp_vmix / dsalt_vmix tendencies), followed by
+the boundary treatment of :290-297 -- ``enforce_boundaries`` is the x-halo exchange of
+``veros_b200.decomp`` (cyclic wrap on one process, NCCL ring between slabs).
+"""
+import torch
+
+from . import _lib, decomp
+from .state import KernelOutput
+
+NEEDS = ("temp", "salt", "taup1", "kappaH", "forc_temp_surface", "forc_salt_surface", "kbot", "dzt", "dzw")
+
+
+def vertmix_tempsalt(state, group=None):
+    vs, settings = state.variables, state.settings
+    for name in NEEDS:
+        if getattr(vs, name, None) is None:
+            raise ValueError(f"vertmix_tempsalt needs variable {name}")
+    N, M, nz = settings.nx + 4, settings.ny + 4, settings.nz
+    if tuple(vs.kappaH.shape) != (N, M, nz) or tuple(vs.forc_temp_surface.shape) != (N, M):
+        raise ValueError("kappaH / forc_temp_surface do not match the grid")
+    if not vs.temp.is_cuda:
+        raise RuntimeError("veros_b200 has no CPU path: the state must live on a CUDA device")
+    for name in ("dtemp_vmix", "dsalt_vmix"):
+        if getattr(vs, name, None) is None:
+            setattr(vs, name, torch.empty((N, M, nz), dtype=torch.float64, device=state.device))
+    desc = _lib.VmixDescriptor(nx_tot=N, ny_tot=M, nz=nz, flags=0, dt_tracer=float(settings.dt_tracer))
+    operands = [vs.temp, vs.salt, vs.taup1, vs.kappaH, vs.forc_temp_surface, vs.forc_salt_surface, vs.kbot,
+                vs.dzt, vs.dzw]
+    results = [vs.temp, vs.salt, vs.dtemp_vmix, vs.dsalt_vmix]  # operand_output_aliases {0: 0, 1: 1}
+    _lib.call("veros_b200_vertmix_tempsalt_f64", [int(t.data_ptr()) for t in operands + results], desc,
+              torch.cuda.current_stream(state.device).cuda_stream)
+    decomp.exchange_halos_x([vs.temp, vs.salt], cyclic=bool(getattr(settings, "enable_cyclic_x", False)),
+                            group=group, level=vs.taup1_host)
+    return KernelOutput(dtemp_vmix=vs.dtemp_vmix, temp=vs.temp, dsalt_vmix=vs.dsalt_vmix, salt=vs.salt)
