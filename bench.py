@@ -306,6 +306,33 @@ def main():
     torch.cuda.synchronize()
     op_ms = {n: sum(e[q].elapsed_time(e[q + 1]) for e in oev) / ksteps for q, n in enumerate(names)}
 
+    # ---- the step after the path: vertmix_tempsalt on the same tracers -------------
+    from veros_b200 import thermodynamics
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7)
+    N_, M_ = nx + 4, ny + 4
+    vmix_fields = dict(
+        kappaH=torch.rand((N_, M_, nz), dtype=torch.float64, device=dev, generator=gen) * 1e-3,
+        forc_temp_surface=(torch.rand((N_, M_), dtype=torch.float64, device=dev, generator=gen) - 0.5) * 1e-5,
+        forc_salt_surface=(torch.rand((N_, M_), dtype=torch.float64, device=dev, generator=gen) - 0.5) * 1e-6,
+    )
+    for s_ in states:
+        for k_, v_ in vmix_fields.items():
+            setattr(s_.variables, k_, v_)
+        s_.settings.enable_cyclic_x = False  # kernel only: the exchange is timed with the step above
+    vev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(ksteps)]
+    thermodynamics.vertmix_tempsalt(states[0])  # the reference-facing call once (allocates the tendencies)
+    for s_ in states[1:]:
+        s_.variables.dtemp_vmix, s_.variables.dsalt_vmix = states[0].variables.dtemp_vmix, states[0].variables.dsalt_vmix
+    vplans = [thermodynamics.VertmixPlan(s_) for s_ in states]
+    for k in range(ksteps):
+        vev[k][0].record()
+        vplans[k % replicas]()
+        vev[k][1].record()
+    torch.cuda.synchronize()
+    vmix_ms = sum(e[0].elapsed_time(e[1]) for e in vev) / ksteps
+    VMIX_BYTES = 56  # R temp,salt@taup1 16 + kappaH 8; W temp,salt 16 + dtemp_vmix,dsalt_vmix 16
+
     peak, peak_src = load_peaks()
     step_bytes = algorithmic_bytes_per_cell(energy)
     step_gbs = cells * step_bytes / (ms_step * 1e-3) / 1e9
@@ -331,6 +358,10 @@ def main():
     }
     step_roofline = {"bytes_per_cell": step_bytes, "achieved": step_gbs, "peak": peak, "unit": "GB/s",
                      "frac": step_gbs / peak, "kernels_ms": kern_ms, "standalone_ops_ms": op_ms}
+    next_ops = {"vertmix_tempsalt": {"ms": vmix_ms, "algorithmic_bytes_per_cell": VMIX_BYTES,
+                                     "achieved_gbs": cells * VMIX_BYTES / (vmix_ms * 1e-3) / 1e9,
+                                     "frac": cells * VMIX_BYTES / (vmix_ms * 1e-3) / 1e9 / peak,
+                                     "note": "the step after the path (SURVEY.md 8f rank 1), one kernel, not part of `value`"}}
     if args.profile:
         if rank == 0:
             sampler.stop()
@@ -342,6 +373,7 @@ def main():
     # ---- end to end: host buffers in, host buffers out ----------------------------------------------
     del states[1:]
     torch.cuda.empty_cache()
+    hs = None
     if args.no_e2e or cells > 20_000_000:
         clocks = sampler.stop() if rank == 0 else None
         e2e = None  # the pinned staging buffers of this leg would be tens of GB
@@ -403,7 +435,7 @@ def main():
                        f"no replica is touched twice in a row") if replicas > 1 else
                       f"inputs larger than L2: one state of {state_bytes / 1e6:.0f} MB streamed per step",
             },
-            "roofline": roofline, "step_roofline": step_roofline, "cpu_baseline": base, "e2e": e2e,
+            "roofline": roofline, "step_roofline": step_roofline, "next_ops": next_ops, "cpu_baseline": base, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if extra:

@@ -327,7 +327,7 @@ __device__ __forceinline__ void phase_c(const UpdConst& u, const TileBuf& b, con
         const int ks = b.ksv[q];
         if (j >= 2 && j < u.M - 2 && ks >= 0) {
             const int o = q * u.pitch;
-            dgtsv_column<NTR>(ks, u.nz, 1, b.L + o, b.D + o, b.U + o, b.R[0] + o, b.R[NTR - 1] + o);
+            dgtsv_column<NTR>(ks, u.nz, b.L + o, b.D + o, b.U + o, b.R[0] + o, b.R[NTR - 1] + o);
         }
     }
 }

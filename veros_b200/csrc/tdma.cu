@@ -21,7 +21,7 @@ solve_implicit_kernel(int ncol, int nz, int cols_per_tile, int pitch, const doub
                       double* __restrict__ out) {
     extern __shared__ double smem[];
     const int tile_elems = cols_per_tile * pitch;
-    double* L = smem;
+    double* L = smem + 1;  // dgtsv_column may touch one element before / after each column (never uses it)
     double* D = L + tile_elems;
     double* U = D + tile_elems;
     double* R = U + tile_elems;
@@ -55,7 +55,7 @@ solve_implicit_kernel(int ncol, int nz, int cols_per_tile, int pitch, const doub
         const int o = col * pitch;
         // rows below the first water row are identity rows with zero rhs: they do not change any
         // later row bitwise (fact * 0 terms), so the elimination starts at the first water row
-        dgtsv_column<1>(kfirst[col], nz, 1, L + o, D + o, U + o, R + o, nullptr);
+        dgtsv_column<1>(kfirst[col], nz, L + o, D + o, U + o, R + o, nullptr);
     }
     __syncthreads();
 
@@ -76,7 +76,7 @@ void launch_solve_implicit(cudaStream_t s, int ncol, int nz, const double* a, co
     // small problems: keep at least ~2 CTAs per SM busy
     const int want_tiles = 2 * 148;
     if ((ncol + cols - 1) / cols < want_tiles) cols = max(1, (ncol + want_tiles - 1) / want_tiles);
-    const size_t smem = (size_t)4 * 8 * cols * pitch + sizeof(int) * cols;
+    const size_t smem = (size_t)4 * 8 * cols * pitch + sizeof(int) * cols + 24;  // + the two guard elements
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(solve_implicit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

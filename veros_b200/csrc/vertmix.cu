@@ -91,7 +91,7 @@ vertmix_kernel(const VmixArgs a, const int cols, const int pitch) {
             const int ks = ksv[q];
             if (j >= 2 && j < M - 2 && ks >= 0) {
                 const int o = q * pitch;
-                dgtsv_column<2>(ks, nz, 1, L + o, D + o, U + o, R0 + o, R1 + o);
+                dgtsv_column<2>(ks, nz, L + o, D + o, U + o, R0 + o, R1 + o);
             }
         }
     }

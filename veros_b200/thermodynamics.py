@@ -17,7 +17,7 @@ from .state import KernelOutput
 NEEDS = ("temp", "salt", "taup1", "kappaH", "forc_temp_surface", "forc_salt_surface", "kbot", "dzt", "dzw")
 
 
-def vertmix_tempsalt(state, group=None):
+def _arguments(state):
     vs, settings = state.variables, state.settings
     for name in NEEDS:
         if getattr(vs, name, None) is None:
@@ -34,8 +34,35 @@ def vertmix_tempsalt(state, group=None):
     operands = [vs.temp, vs.salt, vs.taup1, vs.kappaH, vs.forc_temp_surface, vs.forc_salt_surface, vs.kbot,
                 vs.dzt, vs.dzw]
     results = [vs.temp, vs.salt, vs.dtemp_vmix, vs.dsalt_vmix]  # operand_output_aliases {0: 0, 1: 1}
-    _lib.call("veros_b200_vertmix_tempsalt_f64", [int(t.data_ptr()) for t in operands + results], desc,
-              torch.cuda.current_stream(state.device).cuda_stream)
+    return [int(t.data_ptr()) for t in operands + results], desc
+
+
+def vertmix_tempsalt(state, group=None):
+    vs, settings = state.variables, state.settings
+    ptrs, desc = _arguments(state)
+    _lib.call("veros_b200_vertmix_tempsalt_f64", ptrs, desc, torch.cuda.current_stream(state.device).cuda_stream)
     decomp.exchange_halos_x([vs.temp, vs.salt], cyclic=bool(getattr(settings, "enable_cyclic_x", False)),
                             group=group, level=vs.taup1_host)
     return KernelOutput(dtemp_vmix=vs.dtemp_vmix, temp=vs.temp, dsalt_vmix=vs.dsalt_vmix, salt=vs.salt)
+
+
+class VertmixPlan:
+    """The kernel of `vertmix_tempsalt(state)` with the argument marshalling done once (cf.
+    isoneutral.StepPlan): one foreign-function call per invocation, no boundary exchange."""
+
+    def __init__(self, state):
+        import ctypes
+
+        self.state = state
+        ptrs, desc = _arguments(state)
+        self._arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        self._opaque = bytes(desc)
+        self._fn = _lib.lib().veros_b200_vertmix_tempsalt_f64
+        self._err = _lib.lib().veros_b200_last_error
+        self._void_p = ctypes.c_void_p
+
+    def __call__(self):
+        self._fn(self._void_p(torch.cuda.current_stream(self.state.device).cuda_stream), self._arr, self._opaque,
+                 len(self._opaque))
+        if self._err():
+            _lib.check_error("veros_b200_vertmix_tempsalt_f64")
