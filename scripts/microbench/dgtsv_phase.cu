@@ -13,7 +13,7 @@
 
 using namespace vb;
 
-__global__ void __launch_bounds__(128, 6) phase(double* out, int nz, int cols, int iters, int solve) {
+__global__ void __launch_bounds__(128, 6) phase(double* out, int nz, int cols, int iters, int solve, int rotate) {
     extern __shared__ double sm[];
     const int pitch = nz | 1;
     const int tile = cols * pitch;
@@ -35,8 +35,9 @@ __global__ void __launch_bounds__(128, 6) phase(double* out, int nz, int cols, i
             R1[s] = 35.0 + 1e-3 * (idx % 7);
         }
         __syncthreads();
-        if (solve && threadIdx.x < cols) {
-            const int o = threadIdx.x * pitch;
+        const int vt = (threadIdx.x + 128 - (rotate ? 32 * ((blockIdx.x / 148) & 3) : 0)) & 127;
+        if (solve && vt < cols) {
+            const int o = vt * pitch;
 #ifdef OLD_DGTSV
             dgtsv_column<2>(0, nz, 1, L + o, D + o, U + o, R0 + o, R1 + o);
 #else
@@ -61,6 +62,7 @@ int main(int argc, char** argv) {
     int mhz;
     cudaDeviceGetAttribute(&mhz, cudaDevAttrClockRate, 0);
     const int iters = 200;
+    const int rotate = argc > 2 ? atoi(argv[2]) : 0;  // 1: the solver warp rotates with the CTA's launch position
     for (int ctas = 1; ctas <= 6; ctas += (ctas < 2 ? 1 : 2)) {
         for (int cols : {4, 12, 24, 32}) {
             const size_t smem = 8 * ((size_t)5 * cols * (nz | 1) + 4);
@@ -70,9 +72,9 @@ int main(int argc, char** argv) {
                 cudaEvent_t e0, e1;
                 cudaEventCreate(&e0);
                 cudaEventCreate(&e1);
-                phase<<<148 * ctas, 128, smem>>>(out, nz, cols, 5, solve);
+                phase<<<148 * ctas, 128, smem>>>(out, nz, cols, 5, solve, rotate);
                 cudaEventRecord(e0);
-                phase<<<148 * ctas, 128, smem>>>(out, nz, cols, iters, solve);
+                phase<<<148 * ctas, 128, smem>>>(out, nz, cols, iters, solve, rotate);
                 cudaEventRecord(e1);
                 cudaEventSynchronize(e1);
                 cudaEventElapsedTime(&ms[solve], e0, e1);
