@@ -26,6 +26,7 @@ TARGETS = {
     "veros_b200_iso_pre_f64": "veros_b200_iso_pre_f64",
     "veros_b200_iso_diffusion_f64": "veros_b200_iso_diffusion_f64",
     "veros_b200_iso_step_f64": "veros_b200_iso_step_f64",
+    "veros_b200_vertmix_tempsalt_f64": "veros_b200_vertmix_tempsalt_f64",
     # the reference's own target names, served by the z-major compatible kernels (shim below)
     "tdma_cuda_double": "veros_b200_tdma_zmajor_f64",
     "tdma_cuda_float": "veros_b200_tdma_zmajor_f32",
