@@ -125,6 +125,7 @@ setup_kernel(const Grid g, const double dt, double* base) {
     const Tables t = tables_at(base, N, M, nz);
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
+    if (tid < 4) t.counters[tid] = 0u;
     for (int k = tid; k < nz; k += nth) {
         LevTab e;
         e.d4zt = make_divisor(4.0 * g.dzt[k]);
@@ -173,28 +174,46 @@ constexpr int kPreBlock = 128;
 // 16 slopes over two launches (east+north / top) halves the live state per thread, which raises the
 // register-limited occupancy of this latency-bound kernel; the price is a second read of T and S.
 template <int EOS, bool FLUX, int FACES>
-__global__ void __launch_bounds__(kPreBlock)
+__global__ void __launch_bounds__(kPreBlock, FACES == 7 ? 3 : 4)
 iso_pre_kernel(const PreArgs a) {
     constexpr bool doE = (FACES & 1) != 0, doN = (FACES & 2) != 0, doT = (FACES & 4) != 0;
     const int N = a.g.N, M = a.g.M, nz = a.g.nz;
-    const int i = blockIdx.y;
     const Tables tb = tables_at(a.tables, N, M, nz);
     const int plane_cells = M * nz;
     const int nchunks = (plane_cells + kPreBlock - 1) / kPreBlock;
+    const int total = nchunks * N;
     const int tau = *a.tau;
     const double* __restrict__ T = a.temp + tau;
     const double* __restrict__ S = a.salt + tau;
-    // Persistent over the chunks of its plane: while chunk n is computed (thousands of cycles of FP64
-    // work per warp) the lines chunk n+1 will touch are pulled into L2, so its loads cost an L2 hit
-    // instead of a DRAM round trip -- with ~12 resident warps per SM nothing else hides that latency.
-    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    // One resident wave of persistent CTAs pulls 128-cell chunks (plane-major) from a work counter, so the
+    // kernel has no partial last wave and no CTA ends up with one chunk more than another (a chunk is
+    // thousands of cycles).  The counter is read two chunks ahead: the atomic's latency hides behind a
+    // chunk's arithmetic, and while chunk n is computed the lines chunk n+1 will touch are pulled into L2,
+    // so its loads cost an L2 hit instead of a DRAM round trip -- with ~16 resident warps per SM nothing
+    // else hides that latency.
+    unsigned int* counter = tb.counters + (doE ? 0 : 1);  // the two launches of a split call do not share one
+    __shared__ int s_fetch[2];
+    if (threadIdx.x == 0) {
+        s_fetch[0] = (int)atomicAdd(counter, 1u);
+        s_fetch[1] = (int)atomicAdd(counter, 1u);
+    }
+    __syncthreads();
+    int g = s_fetch[0], gnext = s_fetch[1];
+    int slot = 0;
+    while (g < total) {
+    unsigned int fetched = 0u;
+    if (threadIdx.x == 0) fetched = atomicAdd(counter, 1u);  // chunk after next; consumed at the end of this one
+    const int i = g / nchunks;
+    const int chunk = g - i * nchunks;
     const int p0 = chunk * kPreBlock;
-    {
-        const int pn = p0 + (int)gridDim.x * kPreBlock + (int)threadIdx.x;
+    if (gnext < total) {
+        const int in = gnext / nchunks;
+        const int pn = (gnext - in * nchunks) * kPreBlock + (int)threadIdx.x;
         if (pn < plane_cells) {
             auto pf = [](const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); };
             const size_t pl = (size_t)plane_cells;
-            const size_t cx = (size_t)i * pl + pn;
+            const size_t cx = (size_t)in * pl + pn;
+            const int i = in;  // the prefetched chunk's plane decides which neighbour planes exist
             pf(T + cx * 3); pf(S + cx * 3);
             pf(a.K_iso + cx); pf(a.maskT + cx); pf(a.maskU + cx); pf(a.maskV + cx); pf(a.maskW + cx);
             if (i + 1 < N) { pf(T + (cx + pl) * 3); pf(S + (cx + pl) * 3); pf(a.K_iso + cx + pl); pf(a.maskW + cx + pl); pf(a.maskT + cx + pl); }
@@ -203,7 +222,7 @@ iso_pre_kernel(const PreArgs a) {
         }
     }
     const int p = p0 + threadIdx.x;
-    if (p >= plane_cells) continue;
+    if (p < plane_cells) {
     const int j = p / nz;
     const int k = p - j * nz;
     const size_t plane = (size_t)M * nz;
@@ -488,27 +507,46 @@ iso_pre_kernel(const PreArgs a) {
             if (doT) a.flux[t][2][c] = fl[t][2];
         }
     }
+    }  // cell
+    if (threadIdx.x == 0) s_fetch[slot] = (int)fetched;
+    __syncthreads();
+    g = gnext;
+    gnext = s_fetch[slot];
+    slot ^= 1;
     }  // chunk loop
 }
 
+// One resident wave: CTAs per SM of this instantiation x SMs, never more CTAs than chunks.
+template <typename K>
+static unsigned resident_grid(K kernel, int total_chunks) {
+    int per_sm = 0, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPreBlock, 0) != cudaSuccess || per_sm < 1) per_sm = 3;
+    return (unsigned)std::max(1, std::min(total_chunks, per_sm * sms));
+}
+
 template <int EOS, bool FLUX>
-static void launch_pre_variant(cudaStream_t s, const PreArgs& a, dim3 grid) {
+static void launch_pre_variant(cudaStream_t s, const PreArgs& a, int total_chunks) {
     static const bool force_single = getenv("VEROS_B200_PRE_SINGLE") != nullptr;  // tuning knob
     // measured (profiles/): the split is +3 % on the 1 degree grid, neutral at 1 M cells, and costs one
     // launch, which small grids cannot afford
     const bool single = force_single || (size_t)a.g.N * a.g.M * a.g.nz < 500000;
     if (single) {
-        iso_pre_kernel<EOS, FLUX, 7><<<grid, kPreBlock, 0, s>>>(a);
+        static const unsigned full = resident_grid(iso_pre_kernel<EOS, FLUX, 7>, 1 << 30);
+        iso_pre_kernel<EOS, FLUX, 7><<<std::min(full, (unsigned)total_chunks), kPreBlock, 0, s>>>(a);
         count_launch();
     } else {
-        iso_pre_kernel<EOS, FLUX, 3><<<grid, kPreBlock, 0, s>>>(a);
-        iso_pre_kernel<EOS, FLUX, 4><<<grid, kPreBlock, 0, s>>>(a);
+        static const unsigned full3 = resident_grid(iso_pre_kernel<EOS, FLUX, 3>, 1 << 30);
+        static const unsigned full4 = resident_grid(iso_pre_kernel<EOS, FLUX, 4>, 1 << 30);
+        iso_pre_kernel<EOS, FLUX, 3><<<std::min(full3, (unsigned)total_chunks), kPreBlock, 0, s>>>(a);
+        iso_pre_kernel<EOS, FLUX, 4><<<std::min(full4, (unsigned)total_chunks), kPreBlock, 0, s>>>(a);
         count_launch(2);
     }
 }
 
 template <int EOS>
-static void launch_pre_eos(cudaStream_t s, const PreArgs& a, dim3 grid) {
+static void launch_pre_eos(cudaStream_t s, const PreArgs& a, int grid) {
     if (a.with_flux)
         launch_pre_variant<EOS, true>(s, a, grid);
     else
@@ -531,8 +569,7 @@ void launch_iso_pre(cudaStream_t s, const PreArgs& a0, bool profile) {
         if (!check_launch("eos5_kernel")) return;
     }
     const int nchunks = (M * nz + kPreBlock - 1) / kPreBlock;
-    const int per_plane = std::max(1, std::min(nchunks, (1332 + N - 1) / N));  // ~3 waves of 3 CTAs/SM in total
-    dim3 grid(per_plane, N);
+    const int grid = nchunks * N;  // chunks in total; the launch is one resident wave pulling them
     if (profile) prof_mark(s, 1);
     switch (a.eos) {
     case 1: launch_pre_eos<1>(s, a, grid); break;

@@ -34,11 +34,12 @@ struct Tables {
     const RowTab* row;
     const XTab* xt;
     const CellTab* cell;
+    unsigned int* counters;  // 4 work counters, zeroed by setup_kernel (dynamic chunk scheduling of the slope kernel)
 };
 
 __host__ __device__ inline size_t tables_doubles(int N, int M, int nz) {
     return (size_t)nz * (sizeof(LevTab) / 8) + (size_t)M * (sizeof(RowTab) / 8) + (size_t)N * (sizeof(XTab) / 8) +
-           (size_t)N * M * (sizeof(CellTab) / 8);
+           (size_t)N * M * (sizeof(CellTab) / 8) + 2;
 }
 
 __host__ __device__ inline Tables tables_at(double* base, int N, int M, int nz) {
@@ -51,6 +52,7 @@ __host__ __device__ inline Tables tables_at(double* base, int N, int M, int nz) 
     t.row = row;
     t.xt = xt;
     t.cell = cell;
+    t.counters = reinterpret_cast<unsigned int*>(cell + (size_t)N * M);
     return t;
 }
 
