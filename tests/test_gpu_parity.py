@@ -533,3 +533,82 @@ def test_vertmix_tempsalt_errors(dev):
         thermodynamics.vertmix_tempsalt(gs)
     with pytest.raises(RuntimeError):  # truncated descriptor: the library latches an error instead of launching
         _lib.call("veros_b200_vertmix_tempsalt_f64", [0] * 13, bytes(8), 0)
+
+
+# ------------------------------------------------------------------ special values through the fast solve path
+def _same_bits(x, ref):
+    """Bitwise agreement up to NaN payloads: equal values, equal zero signs, NaNs in the same places."""
+    x, ref = np.asarray(x), np.asarray(ref)
+    nan = np.isnan(ref)
+    return (np.array_equal(np.isnan(x), nan) and np.array_equal(x[~nan], ref[~nan])
+            and np.array_equal(np.signbit(x[~nan]), np.signbit(ref[~nan])))
+
+
+def test_solve_implicit_special_values_match_dgtsv_replay(dev):
+    """The column solve runs ordinary levels in straight-line loops (one reciprocal per pivot, three-instruction
+    quotients) and hands over to the verbatim dgtsv loop at the first level that is not ordinary.  Zeros of both
+    signs, subnormals, huge and tiny magnitudes, infinities, NaNs and interchanges, sprinkled over otherwise well
+    conditioned columns, must give the oracle's dgtsv replay bit for bit, including the sign of zeros."""
+    from oracle import oracle
+    from veros_b200 import utilities
+
+    rng = np.random.default_rng(11)
+    ncol, nz = 600, 37
+    a = -rng.uniform(0.1, 1.0, (ncol, 1, nz))
+    c = -rng.uniform(0.1, 1.0, (ncol, 1, nz))
+    b = 1.0 - a - c
+    d = rng.standard_normal((ncol, 1, nz)) * 10.0
+    specials = [0.0, -0.0, 5e-324, -3e-310, 1e-300, -1e300, 1e308, np.inf, -np.inf, np.nan, 1e-170, 7e200]
+    for arr in (a, b, c, d):  # ~4 % special entries per array; the first 100 columns stay clean
+        hit = rng.random(arr.shape) < 0.04
+        hit[:100] = False
+        arr[hit] = rng.choice(specials, size=int(hit.sum()))
+    b[100:200] *= rng.choice([1.0, 1e-3], size=(100, 1, nz))  # weak diagonals: interchanges
+    kbot = rng.integers(0, nz + 1, size=(ncol, 1)).astype(np.int32)
+    ks = kbot - 1
+    kk = np.arange(nz)[None, None, :]
+    land = (ks >= 0)[:, :, None]
+    water = land & (kk >= ks[:, :, None])
+    edge = land & (kk == ks[:, :, None])
+    with np.errstate(all="ignore"):
+        ref = oracle.solve_implicit(a, b, c, d, water, edge)
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    got = utilities.solve_implicit(t(a), t(b), t(c), t(d), t(water), t(edge)).cpu().numpy()
+    assert np.isnan(ref).any() and np.isinf(ref[~np.isnan(ref)]).any()  # the specials did reach the solutions
+    assert _same_bits(got, ref)
+
+
+def test_vertmix_extreme_values_match_oracle(dev):
+    """Same, through the two-right-hand-side instance inside vertmix_kernel: zero and negative kappaH (zero
+    couplings, interchanges), exactly zero, tiny and huge (finite, normal) tracer values.  The coefficient
+    assembly around the solve divides by grid metrics with the three-instruction recipe, which is the IEEE
+    quotient for zero or normal finite numerators only (csrc/strict.cuh) -- so no subnormals / non-finite values
+    here, and zeros are compared by value."""
+    from oracle import oracle
+    from veros_b200 import synthetic, thermodynamics
+    from veros_b200.state import IsoState
+
+    nx, ny, nz = 30, 26, 21
+    base = synthetic.make_workload("bench_1M", nx=nx, ny=ny, nz=nz)
+    rng = np.random.default_rng(3)
+    N, M = nx + 4, ny + 4
+    st = {k: base[k] for k in ("kbot", "taup1", "dt_tracer", "dzt", "dzw")}
+    st["enable_cyclic_x"] = False
+    st["temp"], st["salt"] = base["temp"].copy(), base["salt"].copy()
+    kap = np.abs(rng.standard_normal((N, M, nz))) * 1e-3
+    kap[rng.random(kap.shape) < 0.3] = 0.0
+    kap[rng.random(kap.shape) < 0.05] *= -40.0
+    st["kappaH"] = kap
+    specials = [0.0, 1e-250, -1e-200, 1e200, -1e250]
+    for name in ("temp", "salt"):
+        hit = rng.random(st[name].shape) < 0.02
+        st[name][hit] = rng.choice(specials, size=int(hit.sum()))
+    st["forc_temp_surface"] = rng.standard_normal((N, M)) * 1e-5
+    st["forc_salt_surface"] = np.zeros((N, M))
+    with np.errstate(all="ignore"):
+        ref = oracle.vertmix_tempsalt(copy_state(st))
+    gs = IsoState.from_numpy(st, dev, strict=False)
+    gs.variables.update(thermodynamics.vertmix_tempsalt(gs))
+    got = gs.to_numpy(["temp", "salt", "dtemp_vmix", "dsalt_vmix"])
+    for k, v in got.items():
+        assert np.array_equal(v, ref[k], equal_nan=True), k
