@@ -96,6 +96,10 @@ static size_t drd_doubles(const VerosB200IsoDescriptor* d) {
     return d->eq_of_state_type == 5 ? (size_t)2 * d->nx_tot * d->ny_tot * d->nz : 0;
 }
 static size_t pre_ws_doubles(const VerosB200IsoDescriptor* d) { return tabs_doubles(d) + drd_doubles(d); }
+// fused step: contiguous copies of int_drhodT/S[..., tau] (PreArgs::stage)
+static size_t step_stage_doubles(const VerosB200IsoDescriptor* d) {
+    return d->enable_conserve_energy ? (size_t)2 * d->nx_tot * d->ny_tot * d->nz : 0;
+}
 
 }  // namespace vb
 
@@ -157,6 +161,9 @@ void veros_b200_iso_pre_f64(void* stream, void** B, const char* opaque, size_t l
     a.drdT = a.tables + tabs_doubles(d);
     a.drdS = a.drdT + n3;
     a.with_flux = 0;
+    a.with_stage = 0;
+    a.stage[0] = a.stage[1] = nullptr;
+    a.stage_src[0] = a.stage_src[1] = nullptr;
     for (int t = 0; t < 2; ++t)
         for (int q = 0; q < 3; ++q) a.flux[t][q] = nullptr;
     a.eos = d->eq_of_state_type;
@@ -201,6 +208,7 @@ void veros_b200_iso_diffusion_f64(void* stream, void** B, const char* opaque, si
     a.skip_west_ring = (d->flags & VEROS_B200_FLAG_NO_WEST_RING) ? 1 : 0;
     a.skip_east_ring = (d->flags & VEROS_B200_FLAG_NO_EAST_RING) ? 1 : 0;
     a.fluxes_ready = 0;
+    a.stage_x[0] = a.stage_x[1] = nullptr;
     a.dt_tracer = d->dt_tracer;
     a.grav = d->grav;
     a.rho_0 = d->rho_0;
@@ -239,7 +247,8 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     p.K_11 = (double*)B[40];
     p.K_22 = (double*)B[41];
     p.K_33 = (double*)B[42];
-    p.tables = ws + diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 2);  // behind the flux/scratch arrays
+    double* stage = ws + diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 2);  // behind the flux/scratch arrays
+    p.tables = stage + step_stage_doubles(d);
     p.tables_ready = 1;
     p.dt_tracer = d->dt_tracer;
     p.drdT = p.tables + tabs_doubles(d);
@@ -250,6 +259,11 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     p.with_flux = 1;
     for (int t = 0; t < 2; ++t)
         for (int q = 0; q < 3; ++q) p.flux[t][q] = ws + (size_t)(3 * t + q) * n3;
+    p.with_stage = energy ? 1 : 0;
+    p.stage_src[0] = (const double*)B[29];
+    p.stage_src[1] = (const double*)B[30];
+    p.stage[0] = energy ? stage : nullptr;
+    p.stage[1] = energy ? stage + n3 : nullptr;
     p.eos = d->eq_of_state_type;
     p.K_iso_steep = d->K_iso_steep;
     p.iso_slopec = d->iso_slopec;
@@ -285,6 +299,8 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     a.skip_west_ring = (d->flags & VEROS_B200_FLAG_NO_WEST_RING) ? 1 : 0;
     a.skip_east_ring = (d->flags & VEROS_B200_FLAG_NO_EAST_RING) ? 1 : 0;
     a.fluxes_ready = 1;
+    a.stage_x[0] = p.stage[0];
+    a.stage_x[1] = p.stage[1];
     a.tables = p.tables;
     a.dt_tracer = d->dt_tracer;
     a.grav = d->grav;
@@ -340,7 +356,7 @@ size_t veros_b200_iso_diffusion_workspace_bytes(const char* opaque, size_t len) 
 size_t veros_b200_iso_step_workspace_bytes(const char* opaque, size_t len) {
     const auto* d = unpack<VerosB200IsoDescriptor>(opaque, len, "iso_step_workspace_bytes: bad descriptor");
     if (!d) return 0;
-    return 8 * (pre_ws_doubles(d) + diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 2));
+    return 8 * (pre_ws_doubles(d) + diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 2) + step_stage_doubles(d));
 }
 
 int veros_b200_last_error(void) { return g_err.load(); }

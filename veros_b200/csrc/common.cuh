@@ -35,6 +35,11 @@ struct PreArgs {
     double two_rd, m2c0, s_max;  // taper constants (filled by launch_iso_pre)
     double* flux[2][3];   // [temp|salt][east|north|top] outputs when with_flux
     int with_flux;
+    // fused step with energy: contiguous copies of int_drhodT/S[..., tau] for the update kernel, which is bound
+    // by the bandwidth its 24-byte-stride reads waste; made by the slope kernel's CTAs between compute chunks
+    const double* stage_src[2];
+    double* stage[2];
+    int with_stage;
     int eos;
     double K_iso_steep, iso_slopec, iso_dslope;
 };
@@ -58,6 +63,7 @@ struct DiffArgs {
     int skew, energy;
     int skip_west_ring, skip_east_ring;  // sub-slab mode (VEROS_B200_FLAG_NO_*_RING)
     int fluxes_ready;  // the fused slope+flux kernel already filled the flux workspace
+    const double* stage_x[2];   // contiguous copies of int_drhodX[..., tau] made by the slope kernel (or null)
     double* tables;    // metric tables (tables.cuh), built by launch_setup_tables
     double dt_tracer, grav, rho_0;
 };

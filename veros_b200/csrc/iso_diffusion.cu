@@ -275,12 +275,15 @@ __device__ __forceinline__ void phase_b(const DiffArgs& a, const Scratch& f, con
             }
             double xc = 0.0, xe = 0.0, xw = 0.0, xn = 0.0, xs = 0.0;
             if (ENERGY) {
-                const double* __restrict__ X = a.t[t].int_drhodX + tau;
-                xc = ldt(X, c);
-                xe = ldt(X, c + plane);
-                xw = ldt(X, c - plane);
-                xn = ldt(X, c + nz);
-                xs = ldt(X, c - nz);
+                // int_drhodX[..., tau]: the step's contiguous copy if there is one, else the strided original
+                const bool st = a.stage_x[t] != nullptr;
+                const double* __restrict__ X = st ? a.stage_x[t] : a.t[t].int_drhodX + tau;
+                const size_t xs_ = st ? 1 : 3;
+                xc = __ldg(X + c * xs_);
+                xe = __ldg(X + (c + plane) * xs_);
+                xw = __ldg(X + (c - plane) * xs_);
+                xn = __ldg(X + (c + nz) * xs_);
+                xs = __ldg(X + (c - nz) * xs_);
             }
             // arithmetic + stores
             if (interior) {
@@ -372,9 +375,11 @@ __device__ __forceinline__ void phase_d(const DiffArgs& a, const Scratch& f, con
                 d0[t] = f.diss[t][c];
                 if (up) d1[t] = f.diss[t][c + 1];
                 if (interior && up) {
-                    const double* __restrict__ X = a.t[t].int_drhodX + tau;
-                    x0[t] = ldt(X, c);
-                    x1[t] = ldt(X, c + 1);
+                    const bool st = a.stage_x[t] != nullptr;
+                    const double* __restrict__ X = st ? a.stage_x[t] : a.t[t].int_drhodX + tau;
+                    const size_t xs_ = st ? 1 : 3;
+                    x0[t] = __ldg(X + c * xs_);
+                    x1[t] = __ldg(X + (c + 1) * xs_);
                     ftc[t] = __ldg(f.ft[t] + c);
                 }
             }

@@ -200,15 +200,54 @@ iso_pre_kernel(const PreArgs a) {
     __syncthreads();
     int g = s_fetch[0], gnext = s_fetch[1];
     int slot = 0;
-    while (g < total) {
+    // With staging, every ninth work item is a copy item: 1024 cells of int_drhodT/S[..., tau] (24-byte stride)
+    // into contiguous scratch.  A copy item is a few DRAM round trips of one CTA while the others compute, so the
+    // copy rides on bandwidth this kernel leaves idle instead of costing the bandwidth-bound update kernel.
+    constexpr int kCopyCells = 8 * kPreBlock;
+    const bool staging = FLUX && doT && a.with_stage;
+    const size_t ncell = (size_t)N * plane_cells;
+    const int ncopy = staging ? (int)((ncell + kCopyCells - 1) / kCopyCells) : 0;
+    const int items = staging ? 9 * ((total + 7) / 8) : total;
+    while (g < items) {
     unsigned int fetched = 0u;
-    if (threadIdx.x == 0) fetched = atomicAdd(counter, 1u);  // chunk after next; consumed at the end of this one
-    const int i = g / nchunks;
-    const int chunk = g - i * nchunks;
+    if (threadIdx.x == 0) fetched = atomicAdd(counter, 1u);  // item after next; consumed at the end of this one
+    int cg = g, cgn = gnext;
+    bool is_copy = false, next_is_chunk = gnext < items;
+    if (staging) {
+        const int q = g / 9, r = g - 9 * q;
+        is_copy = r == 8;
+        cg = is_copy ? q : 8 * q + r;
+        const int qn = gnext / 9, rn = gnext - 9 * qn;
+        next_is_chunk = next_is_chunk && rn != 8;
+        cgn = 8 * qn + rn;
+    }
+    if (is_copy) {
+        if (cg < ncopy) {
+            const size_t c0 = (size_t)cg * kCopyCells + threadIdx.x;
+            double v[2][8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const size_t c = c0 + (size_t)m * kPreBlock;
+                const bool in = c < ncell;
+                v[0][m] = in ? __ldg(a.stage_src[0] + c * 3 + tau) : 0.0;
+                v[1][m] = in ? __ldg(a.stage_src[1] + c * 3 + tau) : 0.0;
+            }
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const size_t c = c0 + (size_t)m * kPreBlock;
+                if (c < ncell) {
+                    a.stage[0][c] = v[0][m];
+                    a.stage[1][c] = v[1][m];
+                }
+            }
+        }
+    } else if (cg < total) {
+    const int i = cg / nchunks;
+    const int chunk = cg - i * nchunks;
     const int p0 = chunk * kPreBlock;
-    if (gnext < total) {
-        const int in = gnext / nchunks;
-        const int pn = (gnext - in * nchunks) * kPreBlock + (int)threadIdx.x;
+    if (next_is_chunk && cgn < total) {
+        const int in = cgn / nchunks;
+        const int pn = (cgn - in * nchunks) * kPreBlock + (int)threadIdx.x;
         if (pn < plane_cells) {
             auto pf = [](const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); };
             const size_t pl = (size_t)plane_cells;
@@ -508,6 +547,7 @@ iso_pre_kernel(const PreArgs a) {
         }
     }
     }  // cell
+    }  // compute chunk
     if (threadIdx.x == 0) s_fetch[slot] = (int)fetched;
     __syncthreads();
     g = gnext;
