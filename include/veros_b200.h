@@ -182,6 +182,26 @@ void veros_b200_clear_error(void);
 void veros_b200_halo_pack_unpack(void* stream, int mode, void** fields, int nfields, int nx_tot, int ny_tot, int nz,
                                  int nlev, int level, void* west_buf, void* east_buf);
 
+/* Multi-GPU plumbing over peer memory (not a custom call): the same exchange without staging buffers or NCCL.
+ * `west_fields` / `east_fields` are the neighbours' arrays and `west_flags` / `east_flags` their flag words, mapped
+ * into this process through CUDA IPC (NULL flags: no neighbour on that side; a single rank on a ring passes its
+ * own pointers).  The kernel announces that this rank's ghost planes may be overwritten, waits for the neighbours
+ * to say the same, stores this rank's edge planes [2,4) / [N-4,N-2) into the neighbours' ghost planes, publishes
+ * completion and returns when both neighbours have published theirs.  `seq` = 1, 2, 3, ... counts the exchanges of
+ * this set of fields (same value on all ranks); `my_flags` = 4 int32 zeroed once, `counter` = 1 uint32 zeroed once.
+ * Every participating rank must enqueue the call; a rank enqueues nothing that needs the exchange before it. */
+void veros_b200_halo_put(void* stream, int seq, void** fields, void** west_fields, void** east_fields, int nfields,
+                         int nx_tot, int nx_tot_west, int ny_tot, int nz, int nlev, int level, void* my_flags,
+                         void* west_flags, void* east_flags, void* counter);
+
+/* CUDA IPC helpers for veros_b200_halo_put.  get_handle: the 64-byte cudaIpcMemHandle_t of the cudaMalloc block
+ * starting at `base` (0 on success).  open_handle: maps a neighbour's block with `device` -- the importing rank's
+ * compute device -- current, peer access enabled lazily; returns the mapped base or NULL (error latched).
+ * close: unmaps. */
+int veros_b200_ipc_get_handle(void* base, void* handle64);
+void* veros_b200_ipc_open_handle(int device, const void* handle64);
+void veros_b200_ipc_close(void* base);
+
 /* Measurement hook: while set (n >= 4, events created by the caller), veros_b200_iso_step_f64 records
  * events[0] on its stream before its first kernel, [1] before the slope+flux kernel, [2] after it and
  * [3] after the update kernel, so a benchmark can time the dominant kernel inside the fused call with

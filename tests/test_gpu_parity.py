@@ -612,3 +612,29 @@ def test_vertmix_extreme_values_match_oracle(dev):
     got = gs.to_numpy(["temp", "salt", "dtemp_vmix", "dsalt_vmix"])
     for k, v in got.items():
         assert np.array_equal(v, ref[k], equal_nan=True), k
+
+
+def test_peer_halo_put_single_rank_ring_matches_torch_path(dev):
+    """veros_b200_halo_put with a rank that is its own neighbour (ring of one): flags hand-shake, edge planes
+    stored into the ghost planes, equal to the torch reference path; repeated exchanges reuse the flag words."""
+    from veros_b200 import decomp
+
+    rng = np.random.default_rng(2)
+    for shape, level in (((14, 9, 7, 3), 1), ((11, 6, 5), None)):
+        a = torch.from_numpy(rng.standard_normal(shape)).to(dev)
+        b = torch.from_numpy(rng.standard_normal(shape)).to(dev)
+        ra, rb = a.clone(), b.clone()
+        ex = decomp.PeerHaloExchange([a, b], level=level, cyclic=True)
+        for rep in range(3):
+            decomp.exchange_halos_x([ra, rb], cyclic=True, level=level)
+            ex()
+            torch.cuda.synchronize()
+            assert torch.equal(a, ra) and torch.equal(b, rb)
+            a[2:4] += 1.0  # change the edges between exchanges
+            ra[2:4] += 1.0
+        assert ex.flags.tolist() == [3, 3, 3, 3]
+    closed = decomp.PeerHaloExchange([a], level=None, cyclic=False)
+    before = a.clone()
+    closed()
+    torch.cuda.synchronize()
+    assert torch.equal(a, before)

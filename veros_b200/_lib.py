@@ -31,6 +31,10 @@ HELPERS = (
     "veros_b200_launch_count",
     "veros_b200_profile_events",
     "veros_b200_halo_pack_unpack",
+    "veros_b200_halo_put",
+    "veros_b200_ipc_get_handle",
+    "veros_b200_ipc_open_handle",
+    "veros_b200_ipc_close",
 )
 
 
@@ -97,6 +101,16 @@ def lib():
     L.veros_b200_halo_pack_unpack.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_void_p, ctypes.c_void_p]
+    L.veros_b200_ipc_get_handle.restype = ctypes.c_int
+    L.veros_b200_ipc_get_handle.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    L.veros_b200_ipc_open_handle.restype = ctypes.c_void_p
+    L.veros_b200_ipc_open_handle.argtypes = [ctypes.c_int, ctypes.c_char_p]
+    L.veros_b200_ipc_close.restype = None
+    L.veros_b200_ipc_close.argtypes = [ctypes.c_void_p]
+    L.veros_b200_halo_put.restype = None
+    L.veros_b200_halo_put.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                      ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)] + \
+        [ctypes.c_int] * 7 + [ctypes.c_void_p] * 4
     L.veros_b200_profile_events.restype = None
     L.veros_b200_profile_events.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
     if L.veros_b200_abi_version() != ABI_VERSION:

@@ -11,6 +11,8 @@ directions, the only ones a (P, 1) decomposition has: one batched NCCL send/recv
 (``torch.distributed.batch_isend_irecv`` = ncclGroupStart/ncclSend/ncclRecv/ncclGroupEnd).  With the
 gloo backend the same code runs on CPU tensors (used by the world_size-2 tests).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -130,6 +132,102 @@ class TracerHaloExchange:
             w.wait()
         self._launch(1, self.recv_w if west is not None else None, self.recv_e if east is not None else None)
         self._check("halo exchange")
+
+
+_IPC_OPEN = {}  # handle bytes -> mapped base address (a block is mapped once per process)
+
+
+def _ipc_export(t):
+    """(handle, offset) of a CUDA tensor: the IPC handle of the allocator block that holds it and the tensor's
+    byte offset inside that block (torch sub-allocates tensors from cudaMalloc'ed segments)."""
+    import ctypes
+
+    from . import _lib
+
+    ptr = t.data_ptr()
+    for seg in torch.cuda.memory_snapshot():
+        if seg["device"] == t.device.index and seg["address"] <= ptr < seg["address"] + seg["total_size"]:
+            if seg.get("is_expandable", False):
+                raise RuntimeError("peer halo exchange needs cudaMalloc-backed tensors (expandable segments are not "
+                                   "exportable through legacy CUDA IPC)")
+            buf = ctypes.create_string_buffer(64)
+            _lib.lib().veros_b200_ipc_get_handle(ctypes.c_void_p(seg["address"]), buf)
+            _lib.check_error("peer halo exchange setup")
+            return bytes(buf.raw), ptr - seg["address"]
+    raise RuntimeError("tensor is not owned by torch's CUDA caching allocator")
+
+
+def _ipc_import(device_index, handle, offset):
+    from . import _lib
+
+    if handle not in _IPC_OPEN:
+        base = _lib.lib().veros_b200_ipc_open_handle(int(device_index), handle)
+        _lib.check_error("peer halo exchange setup")
+        _IPC_OPEN[handle] = int(base)
+    return _IPC_OPEN[handle] + int(offset)
+
+
+class PeerHaloExchange:
+    """The same exchange over peer memory: one kernel per rank stores the edge planes straight into the
+    neighbours' ghost planes through NVLink (csrc/halo.cu, veros_b200_halo_put) -- no staging buffers, no NCCL
+    call, the hand-shake is four flag words per rank.  The neighbours' arrays are mapped once, at construction,
+    through CUDA IPC (handles exchanged with all_gather_object, opened with this rank's device current), so all
+    ranks must live on one node.  A single rank on a ring is its own neighbour."""
+
+    def __init__(self, fields, level=None, cyclic=True, group=None):
+        import ctypes
+
+        from . import _lib
+
+        f0 = fields[0]
+        if not all(f.is_cuda and f.is_contiguous() and f.shape == f0.shape and f.dtype == torch.float64 for f in fields):
+            raise ValueError("fields must be contiguous float64 CUDA tensors of one shape")
+        if (f0.dim() == 4) != (level is not None):
+            raise ValueError("4-D tracers need a time level, 3-D fields must not have one")
+        self.fields, self.group = list(fields), group
+        self.N, self.M, self.nz = f0.shape[:3]
+        self.nlev, self.level = (f0.shape[3], int(level)) if level is not None else (1, 0)
+        self.flags = torch.zeros(4, dtype=torch.int32, device=f0.device)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=f0.device)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        west, east = neighbours(rank, world, cyclic)
+        own = ([f.data_ptr() for f in self.fields], self.flags.data_ptr(), self.N)
+        peers = {rank: own}
+        if world > 1:
+            torch.cuda.synchronize(f0.device)
+            mine = ([_ipc_export(f) for f in self.fields], _ipc_export(self.flags), self.N)
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine, group=group)
+            for r in {west, east} - {None, rank}:
+                handles, flag_handle, n_r = everyone[r]
+                peers[r] = ([_ipc_import(f0.device.index, h, o) for h, o in handles],
+                            _ipc_import(f0.device.index, *flag_handle), n_r)
+        arr = lambda ptrs: (ctypes.c_void_p * len(ptrs))(*ptrs)
+        self._mine = arr(own[0])
+        self._west = arr(peers[west][0]) if west is not None else None
+        self._east = arr(peers[east][0]) if east is not None else None
+        self._west_flags = peers[west][1] if west is not None else None
+        self._east_flags = peers[east][1] if east is not None else None
+        self._n_west = int(peers[west][2]) if west is not None else self.N
+        self._seq = 0
+        self._fn = _lib.lib().veros_b200_halo_put
+        self._check = _lib.check_error
+        self._vp = ctypes.c_void_p
+        if world > 1:
+            dist.barrier(group=group)  # nobody starts exchanging before every mapping exists
+
+    def __call__(self):
+        if self._west is None and self._east is None:
+            return
+        self._seq += 1
+        s = torch.cuda.current_stream(self.fields[0].device).cuda_stream
+        self._fn(self._vp(s), self._seq, self._mine, self._west, self._east, len(self.fields), self.N, self._n_west,
+                 self.M, self.nz, self.nlev, self.level, self._vp(self.flags.data_ptr()),
+                 self._vp(self._west_flags) if self._west_flags is not None else None,
+                 self._vp(self._east_flags) if self._east_flags is not None else None,
+                 self._vp(self.counter.data_ptr()))
+        self._check("peer halo exchange")
 
 
 class OverlappedStepper:
