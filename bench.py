@@ -159,6 +159,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the global_1deg side measurement")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (forced above 20 M cells per rank)")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: halo exchange by stores into the neighbours' memory over NVLink (one kernel per rank, CUDA "
+                         "IPC mappings) or by pack + NCCL send/recv + unpack")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank gets a slab of the named size; strong: the named grid is split over the ranks")
     ap.add_argument("--profile", action="store_true",
@@ -232,8 +235,9 @@ def main():
 
     plans = [isoneutral.StepPlan(s) for s in states]  # argument marshalling done once, as under XLA
     overlap = world > 1 and (args.overlap == "on" or (args.overlap == "auto" and cells >= 3_000_000))
-    steppers = [decomp.OverlappedStepper(s, cyclic=cyclic) for s in states] if overlap else None
-    exchanges = [decomp.TracerHaloExchange([s.variables.temp, s.variables.salt], level=int(st["taup1"]), cyclic=cyclic)
+    steppers = [decomp.OverlappedStepper(s, cyclic=cyclic, halo=args.halo) for s in states] if overlap else None
+    make_exchange = decomp.PeerHaloExchange if args.halo == "peer" else decomp.TracerHaloExchange
+    exchanges = [make_exchange([s.variables.temp, s.variables.salt], level=int(st["taup1"]), cyclic=cyclic)
                  for s in states] if (world > 1 and not overlap) else None
 
     def step(s):
@@ -428,7 +432,8 @@ def main():
             "config": {
                 "workload": name, "nx": nx, "ny": ny, "nz": nz, "cells_per_gpu": cells,
                 "eq_of_state_type": int(st["eq_of_state_type"]), "enable_conserve_energy": energy,
-                "parallelism": f"x-slabs x{world}" + ((" + NCCL ring halo exchange of temp/salt[taup1]" +
+                "parallelism": f"x-slabs x{world}" + (((" + ring halo exchange of temp/salt[taup1] by peer-memory stores over NVLink"
+                                                        if args.halo == "peer" else " + NCCL ring halo exchange of temp/salt[taup1]") +
                                 (", boundary strips first, exchange overlapped with interior" if overlap else ", exchange after the step"))
                                 if world > 1 else ""),
                 "l2": (f"inputs larger than L2: {replicas} state replicas of {state_bytes / 1e6:.0f} MB rotated, "

@@ -235,12 +235,12 @@ class OverlappedStepper:
 
     The slab is processed as three sub-slabs (IsoState.subslab; bit-identical to the whole-slab step):
     the two boundary strips (interior planes 2,3 and N-4,N-3: exactly what the neighbours need) go first
-    on a side stream, the NCCL send/recv of their temp/salt[taup1] planes follows on the communication
-    stream, and the remaining interior runs meanwhile on the caller's stream.  Replaces the sequence
+    on a side stream, the exchange of their temp/salt[taup1] planes (peer-memory stores, or NCCL send/recv)
+    follows on the communication stream, and the remaining interior runs meanwhile on the caller's stream.  Replaces the sequence
     "step, then enforce_boundaries(temp/salt[taup1])" of veros/core/thermodynamics.py:430-432,293-298.
     """
 
-    def __init__(self, state, cyclic=True, group=None):
+    def __init__(self, state, cyclic=True, group=None, halo="peer"):
         N = state.settings.nx + 4
         if N < 12:
             raise ValueError("slab too thin to overlap: needs at least 8 interior planes")
@@ -255,7 +255,8 @@ class OverlappedStepper:
         state.workspace(isoneutral.step_workspace_bytes(state))  # `mid` shares it; keep its address stable
         self.plans = [isoneutral.StepPlan(s) for s in (self.west, self.east, self.mid)]
         vs = state.variables
-        self.exchange = TracerHaloExchange([vs.temp, vs.salt], level=vs.taup1_host, cyclic=cyclic, group=group)
+        make = PeerHaloExchange if halo == "peer" else TracerHaloExchange  # NVLink stores / NCCL send-recv
+        self.exchange = make([vs.temp, vs.salt], level=vs.taup1_host, cyclic=cyclic, group=group)
         self.s_strip = torch.cuda.Stream(state.device)
         self.s_comm = torch.cuda.Stream(state.device)
         self.ev_strips = torch.cuda.Event()
