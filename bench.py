@@ -235,10 +235,19 @@ def main():
 
     plans = [isoneutral.StepPlan(s) for s in states]  # argument marshalling done once, as under XLA
     overlap = world > 1 and (args.overlap == "on" or (args.overlap == "auto" and cells >= 3_000_000))
-    steppers = [decomp.OverlappedStepper(s, cyclic=cyclic, halo=args.halo) for s in states] if overlap else None
-    make_exchange = decomp.PeerHaloExchange if args.halo == "peer" else decomp.TracerHaloExchange
-    exchanges = [make_exchange([s.variables.temp, s.variables.salt], level=int(st["taup1"]), cyclic=cyclic)
-                 for s in states] if (world > 1 and not overlap) else None
+    def build_exchange(halo):
+        steppers_ = [decomp.OverlappedStepper(s, cyclic=cyclic, halo=halo) for s in states] if overlap else None
+        make_exchange = decomp.PeerHaloExchange if halo == "peer" else decomp.TracerHaloExchange
+        exchanges_ = [make_exchange([s.variables.temp, s.variables.salt], level=int(st["taup1"]), cyclic=cyclic)
+                      for s in states] if (world > 1 and not overlap) else None
+        return steppers_, exchanges_
+
+    halo_note = ""
+    try:
+        steppers, exchanges = build_exchange(args.halo)
+    except decomp.PeerSetupError as err:  # raised on all ranks alike (e.g. allocator blocks that cannot be exported)
+        args.halo, halo_note = "nccl", f" (peer-memory mapping unavailable: {err})"
+        steppers, exchanges = build_exchange("nccl")
 
     def step(s):
         q = states.index(s)
@@ -434,7 +443,7 @@ def main():
                 "eq_of_state_type": int(st["eq_of_state_type"]), "enable_conserve_energy": energy,
                 "parallelism": f"x-slabs x{world}" + (((" + ring halo exchange of temp/salt[taup1] by peer-memory stores over NVLink"
                                                         if args.halo == "peer" else " + NCCL ring halo exchange of temp/salt[taup1]") +
-                                (", boundary strips first, exchange overlapped with interior" if overlap else ", exchange after the step"))
+                                (", boundary strips first, exchange overlapped with interior" if overlap else ", exchange after the step") + halo_note)
                                 if world > 1 else ""),
                 "l2": (f"inputs larger than L2: {replicas} state replicas of {state_bytes / 1e6:.0f} MB rotated, "
                        f"no replica is touched twice in a row") if replicas > 1 else

@@ -137,6 +137,11 @@ class TracerHaloExchange:
 _IPC_OPEN = {}  # handle bytes -> mapped base address (a block is mapped once per process)
 
 
+class PeerSetupError(RuntimeError):
+    """The peer-memory mappings could not be established on some rank (raised on every rank alike, so the
+    caller can switch all ranks to the NCCL exchange together)."""
+
+
 def _ipc_export(t):
     """(handle, offset) of a CUDA tensor: the IPC handle of the allocator block that holds it and the tensor's
     byte offset inside that block (torch sub-allocates tensors from cudaMalloc'ed segments)."""
@@ -144,6 +149,8 @@ def _ipc_export(t):
 
     from . import _lib
 
+    if os.environ.get("VEROS_B200_NO_PEER_IPC"):  # test hook: behave as if the blocks could not be exported
+        raise RuntimeError("peer-memory mapping disabled by VEROS_B200_NO_PEER_IPC")
     ptr = t.data_ptr()
     for seg in torch.cuda.memory_snapshot():
         if seg["device"] == t.device.index and seg["address"] <= ptr < seg["address"] + seg["total_size"]:
@@ -196,13 +203,28 @@ class PeerHaloExchange:
         peers = {rank: own}
         if world > 1:
             torch.cuda.synchronize(f0.device)
-            mine = ([_ipc_export(f) for f in self.fields], _ipc_export(self.flags), self.N)
+            try:
+                mine = ([_ipc_export(f) for f in self.fields], _ipc_export(self.flags), self.N)
+            except RuntimeError as err:  # reported through the collective so that all ranks fail together
+                mine = str(err)
             everyone = [None] * world
             dist.all_gather_object(everyone, mine, group=group)
-            for r in {west, east} - {None, rank}:
-                handles, flag_handle, n_r = everyone[r]
-                peers[r] = ([_ipc_import(f0.device.index, h, o) for h, o in handles],
-                            _ipc_import(f0.device.index, *flag_handle), n_r)
+            failed = [f"rank {r}: {e}" for r, e in enumerate(everyone) if isinstance(e, str)]
+            if failed:
+                raise PeerSetupError("; ".join(failed))
+            problem = None
+            try:
+                for r in {west, east} - {None, rank}:
+                    handles, flag_handle, n_r = everyone[r]
+                    peers[r] = ([_ipc_import(f0.device.index, h, o) for h, o in handles],
+                                _ipc_import(f0.device.index, *flag_handle), n_r)
+            except RuntimeError as err:
+                problem = str(err)
+            verdicts = [None] * world
+            dist.all_gather_object(verdicts, problem, group=group)
+            failed = [f"rank {r}: {e}" for r, e in enumerate(verdicts) if e is not None]
+            if failed:
+                raise PeerSetupError("; ".join(failed))
         arr = lambda ptrs: (ctypes.c_void_p * len(ptrs))(*ptrs)
         self._mine = arr(own[0])
         self._west = arr(peers[west][0]) if west is not None else None
