@@ -18,6 +18,10 @@
 //   * slope denominators use the same branch-free reciprocal; the four x- and four y-slopes of a
 //     top face share two of them;
 //   * masks enter as selects folded into the metric factors, never as int->double conversions.
+// Work distribution: one resident wave of persistent CTAs pulls 128-cell chunks from a work counter (no partial
+// last wave, next chunk's lines prefetched into L2); large grids run the horizontal and the top faces as two
+// launches to halve the live state per thread; in the fused step every ninth work item of the top-face launch
+// is a copy item that stages int_drhodT/S[..., tau] contiguously for the update kernel.
 // Slopes/diffusivities agree with the reference to ~1e-15 of their maximum (tests/), not bit for
 // bit (NumPy's SIMD tanh is not reproducible either).  The FLUXES are strict: given the stored Ai_*
 // and K_* they are bit-identical to the reference's expressions (flux_device.cuh).
