@@ -141,6 +141,8 @@ def _primitives():
                                           ws("veros_b200_iso_diffusion_workspace_bytes"))
     _prims["step"] = _make_primitive("veros_b200_iso_step_f64", 12, True, True, ws("veros_b200_iso_step_workspace_bytes"))
     _prims["solve"] = _make_primitive("veros_b200_solve_implicit_f64", 0, True, False, None, fresh_like=(0,))
+    # temp, salt updated in place; dtemp_vmix, dsalt_vmix fresh, shaped like kappaH (operand 3)
+    _prims["vertmix"] = _make_primitive("veros_b200_vertmix_tempsalt_f64", 2, True, False, None, fresh_like=(3, 3))
     return _prims
 
 
@@ -226,7 +228,23 @@ def make_replacements():
     def solve_tridiagonal(a, b, c, d, water_mask, edge_mask):
         return solve_implicit(a, b, c, d, water_mask, edge_mask)
 
-    return dict(isoneutral_diffusion_pre=isoneutral_diffusion_pre, isoneutral_diffusion=isoneutral_diffusion,
+    @veros_kernel
+    def vertmix_tempsalt(state):
+        """veros/core/thermodynamics.py:248-300: one custom call, then the reference's own boundary treatment."""
+        from veros.core import utilities
+        from veros.core.operators import at, update
+
+        vs, st = state.variables, state.settings
+        N, M, nz = vs.kappaH.shape
+        desc = _lib.VmixDescriptor(nx_tot=N, ny_tot=M, nz=nz, flags=0, dt_tracer=st.dt_tracer)
+        ops = [vs.temp, vs.salt, _i32(vs.taup1), vs.kappaH, vs.forc_temp_surface, vs.forc_salt_surface,
+               vs.kbot.astype(jnp.int32), vs.dzt, vs.dzw]
+        temp, salt, dtemp_vmix, dsalt_vmix = P["vertmix"].bind(*ops, descriptor=bytes(desc))
+        temp = update(temp, at[..., vs.taup1], utilities.enforce_boundaries(temp[..., vs.taup1], st.enable_cyclic_x))
+        salt = update(salt, at[..., vs.taup1], utilities.enforce_boundaries(salt[..., vs.taup1], st.enable_cyclic_x))
+        return KernelOutput(dtemp_vmix=dtemp_vmix, temp=temp, dsalt_vmix=dsalt_vmix, salt=salt)
+
+    return dict(vertmix_tempsalt=vertmix_tempsalt, isoneutral_diffusion_pre=isoneutral_diffusion_pre, isoneutral_diffusion=isoneutral_diffusion,
                 isoneutral_skew_diffusion=isoneutral_skew_diffusion, solve_implicit=solve_implicit,
                 solve_tridiagonal=solve_tridiagonal)
 
@@ -250,4 +268,7 @@ def install():
     utilities.solve_implicit = r["solve_implicit"]
     utilities.solve_tridiagonal = r["solve_tridiagonal"]
     operators.solve_tridiagonal = r["solve_tridiagonal"]
+    import veros.core.thermodynamics as thermodynamics
+
+    thermodynamics.vertmix_tempsalt = r["vertmix_tempsalt"]  # looked up as a module global at :440
     return r
