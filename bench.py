@@ -115,7 +115,7 @@ def cpu_baseline(workload, seconds=12.0, threads=None):
         oracle.isoneutral_step(st)
         times.append(time.perf_counter() - t1)
         n += 1
-        if time.perf_counter() - t0 > seconds or n >= 50:
+        if time.perf_counter() - t0 > seconds or n >= 400:
             break
     best = min(times)
     return {
