@@ -15,7 +15,7 @@ using namespace vb;
 
 __global__ void __launch_bounds__(128, 6) phase(double* out, int nz, int cols, int iters, int solve, int rotate) {
     extern __shared__ double sm[];
-    const int pitch = nz | 1;
+    const int pitch = (nz + 1) | 1;
     const int tile = cols * pitch;
     double* L = sm + 1;
     double* D = L + tile;
@@ -65,7 +65,7 @@ int main(int argc, char** argv) {
     const int rotate = argc > 2 ? atoi(argv[2]) : 0;  // 1: the solver warp rotates with the CTA's launch position
     for (int ctas = 1; ctas <= 6; ctas += (ctas < 2 ? 1 : 2)) {
         for (int cols : {4, 12, 24, 32}) {
-            const size_t smem = 8 * ((size_t)5 * cols * (nz | 1) + 4);
+            const size_t smem = 8 * ((size_t)5 * cols * ((nz + 1) | 1) + 4);
             if (smem * ctas > 220 * 1024) continue;
             float ms[2];
             for (int solve = 0; solve < 2; ++solve) {

@@ -474,7 +474,7 @@ update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch
 template <int NTR, bool SKEW, bool ENERGY>
 void launch_update(cudaStream_t s, const DiffArgs& a, const Scratch& f) {
     const int M = a.g.M, N = a.g.N, nz = a.g.nz;
-    const int pitch = nz | 1;
+    const int pitch = (nz + 1) | 1;  // odd (no bank conflicts) and > nz: the element past a column belongs to nobody
     const double fac_diss = 0.5 * a.grav / a.rho_0;  // diffusion.py (core) :19-21, Python float arithmetic
     const double gr = -a.grav / a.rho_0;             // isoneutral/diffusion.py:259,268
     int cols = max(1, 640 / nz);

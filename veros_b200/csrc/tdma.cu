@@ -70,7 +70,7 @@ void launch_solve_implicit(cudaStream_t s, int ncol, int nz, const double* a, co
                            const double* d, const uint8_t* water, const uint8_t* edge, const double* b_edge,
                            const double* d_edge, double* out) {
     if (ncol <= 0 || nz <= 0) return;
-    const int pitch = nz | 1;
+    const int pitch = (nz + 1) | 1;  // odd (no bank conflicts) and > nz: the element past a column belongs to nobody
     int cols = (56 * 1024) / (4 * 8 * pitch);
     cols = max(1, min(cols, 64));
     // small problems: keep at least ~2 CTAs per SM busy

@@ -121,7 +121,7 @@ vertmix_kernel(const VmixArgs a, const int cols, const int pitch) {
 void launch_vertmix(cudaStream_t s, const VmixArgs& a) {
     const int N = a.N, M = a.M, nz = a.nz;
     if (N <= 0 || M <= 0 || nz <= 0) return;
-    const int pitch = nz | 1;
+    const int pitch = (nz + 1) | 1;  // odd (no bank conflicts) and > nz: the element past a column belongs to nobody
     int cols = max(1, 640 / nz);
     cols = min(cols, M);
     const int want_tiles = 4 * 148;  // small grids: spread over the SMs
