@@ -95,6 +95,28 @@ class ClockSampler:
         return out
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """Keep stdout for the one JSON line: native libraries (NCCL prints its version banner there) and stray
+    prints go to stderr for the rest of the run."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def cpu_baseline(workload, seconds=12.0, threads=None):
     """The CPU oracle (oracle/iso_oracle.c, a port of the reference's NumPy path pinned to its golden
     vectors) timed on this host: repeated full steps of the same workload until `seconds` have passed."""
@@ -145,7 +167,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -170,6 +192,7 @@ def main():
                     help="N > 1: hide the halo exchange behind interior compute (auto: slabs of >= 3 M cells; "
                          "below that the two extra boundary-strip passes cost more than the exchange)")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3)
     if args.profile:
         args.no_cpu = args.no_extra = True
@@ -378,7 +401,7 @@ def main():
     if args.profile:
         if rank == 0:
             sampler.stop()
-            print(json.dumps({"profile_only": True, "ms_per_step": ms_step, "kernels_ms": kern_ms}))
+            emit({"profile_only": True, "ms_per_step": ms_step, "kernels_ms": kern_ms})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -454,7 +477,7 @@ def main():
         }
         if extra:
             line["also"] = extra
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
