@@ -1,0 +1,33 @@
+"""bench.py's reference arm runs without a GPU: check the JSON contract of the line it prints (one line on
+stdout, the keys the driver reads, the cpu_baseline / e2e objects of the tier's reference arm)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
+                          "--steps", "1", "--warmup", "1", "--workload", "global_4deg"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["unit"] == "cell-updates/s" and d["dtype"] == "f64" and d["data"] == "synthetic"
+    for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["config"]["workload"] == "global_4deg"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_without_work():
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=60, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
