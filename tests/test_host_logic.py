@@ -109,3 +109,29 @@ def test_oracle_slab_invariance():
         got = oracle.isoneutral_step(part)
         for k in ("temp", "salt", "dtemp_iso", "dsalt_iso", "P_diss_iso", "K_33", "Ai_ez", "Ai_by"):
             assert np.array_equal(got[k][2:-2], ref[k][x0 + 2:x1 + 2]), k
+
+
+def test_vertmix_wrapper_validates_before_touching_the_library():
+    """veros_b200.thermodynamics.vertmix_tempsalt: missing variables and CPU tensors are refused on the host,
+    with the exception types of the reference's own op wrappers (tdma_.py:53-57); a state that carries only the
+    vertmix variables is accepted by IsoState.from_numpy(strict=False)."""
+    import helpers
+    from veros_b200 import thermodynamics
+    from veros_b200.state import IsoState
+
+    st, _ = helpers.load_vmix_golden(helpers.vmix_golden_names()[0])
+    s = IsoState.from_numpy(st, "cpu", strict=False)
+    assert tuple(s.variables.kappaH.shape) == tuple(st["kappaH"].shape)
+    assert tuple(s.variables.forc_temp_surface.shape) == tuple(st["kappaH"].shape[:2])
+    assert not hasattr(s.variables, "K_iso")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        thermodynamics.vertmix_tempsalt(s)
+    del s.variables.forc_salt_surface
+    with pytest.raises(ValueError, match="forc_salt_surface"):
+        thermodynamics.vertmix_tempsalt(s)
+    with pytest.raises(KeyError):  # the isoneutral path needs its own variables
+        IsoState.from_numpy(st, "cpu")
+    s = IsoState.from_numpy(st, "cpu", strict=False)
+    s.variables.kappaH = s.variables.kappaH[:, :, :-1]
+    with pytest.raises(ValueError, match="kappaH"):
+        s.validate(strict=False)
