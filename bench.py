@@ -3,11 +3,20 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
 
-One "step" = one pass of the hot path (veros/core/thermodynamics.py:430-432) over one synthetic
-state; unit of work = one interior grid cell through one step ("cell-update").  Prints ONE JSON line
-(rank 0).  N > 1 is launched by torch.distributed.run, one rank per GPU; every rank owns an x-slab
-of the same size (weak scaling) and exchanges the 2-cell tracer halos with its ring neighbours over
-NCCL after each step.  See DESIGN.md "Measurement" for how each field is obtained.
+One "step" = one pass of the hot path (veros/core/thermodynamics.py:430-432) over one synthetic state; unit of
+work = one interior grid cell through one step ("cell-update").  Prints ONE JSON line (rank 0).
+
+Defaults follow BASELINE.json's north star:
+  * N = 1: the 1 degree global grid (global_1deg, 360 x 160 x 115, TEOS-10, energy on) -- the grid the roofline
+    target is stated on.  `also` carries the other single-GPU configs (bench_1M, global_4deg through a CUDA
+    graph, the ACC grid, the stand-alone column solve on the shapes of benchmarks/tdma_benchmark.py).
+  * N > 1 (torch.distributed.run, one rank per GPU): STRONG scaling of the 0.25 degree grid (global_025deg,
+    1440 x 720 x 80 split into N x-slabs of one consistent global state), the 2-cell tracer halo exchange by
+    peer-memory stores over NVLink, overlapped with the interior compute (boundary strips first), plus a
+    bit-for-bit check of the seam between ranks 0 and 1 against a single-GPU run of the same planes.
+  * --impl reference: the UNMODIFIED reference (NumPy backend) from baseline/_ref on the host cores, on a
+    bounded x-slab sample of the same workload (baseline/numpy_reference.py); rank 0 only.
+See DESIGN.md "Measurement" for how each field is obtained.
 """
 import argparse
 import json
@@ -22,8 +31,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "isoneutral+TDMA cell-updates/s fp64"
 UNIT = "cell-updates/s"
-DEFAULT_WORKLOAD = "bench_1M"  # BASELINE.json configs[1]: isoneutral_benchmark.py, ~1M cells
 L2_BYTES = 126e6
+PRE_BYTES_PER_CELL = 180  # isoneutral_diffusion_pre alone: 28 B read + 152 B written (SURVEY.md 8d)
+SOLVE_BYTES_PER_CELL = 42  # stand-alone solve_implicit: a, b, c, d read + out written + two mask bytes
 
 
 def algorithmic_bytes_per_cell(energy):
@@ -31,7 +41,8 @@ def algorithmic_bytes_per_cell(energy):
     return 276 if energy else 244
 
 
-PRE_BYTES_PER_CELL = 180  # isoneutral_diffusion_pre alone: 28 B read + 152 B written (SURVEY.md 8d)
+def default_workload(world):
+    return "global_1deg" if world == 1 else "global_025deg"
 
 
 def load_peaks():
@@ -117,21 +128,39 @@ def emit(obj):
         os.write(_RESULT_FD, data)
 
 
-def cpu_baseline(workload, seconds=12.0, threads=None):
-    """The CPU oracle (oracle/iso_oracle.c, a port of the reference's NumPy path pinned to its golden
-    vectors) timed on this host: repeated full steps of the same workload until `seconds` have passed."""
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------- CPU legs
+def sample_kwargs(name, target_cells=1_000_000):
+    """A bounded sample of a named workload for the CPU legs: the x-slab [0, nxs) of the same global state
+    (all y, all z, ghost planes included), about `target_cells` interior cells."""
+    from veros_b200 import synthetic
+
+    cfg = synthetic.WORKLOADS[name]
+    per_plane = cfg["ny"] * cfg["nz"]
+    nxs = max(8, min(cfg["nx"], int(round(target_cells / per_plane))))
+    if name == "bench_1M" or nxs == cfg["nx"]:
+        return {}, cfg["nx"]
+    return dict(nx=nxs, x_offset=0, nx_global=cfg["nx"]), nxs
+
+
+def port_baseline(name, kw, seconds=12.0):
+    """The CPU oracle (oracle/iso_oracle.c, a C/OpenMP restatement of the reference's NumPy path pinned to its
+    golden vectors) on ALL host cores: repeated full steps until `seconds` have passed."""
     from oracle import oracle
     from veros_b200 import synthetic
 
-    if threads:
-        oracle.set_num_threads(threads)
+    oracle.set_num_threads(host_cores())  # torchrun exports OMP_NUM_THREADS=1 to its workers
     cores = oracle.num_threads()
-    name, kw = workload
     st = synthetic.make_workload(name, **kw)
     cells = st["nx"] * st["ny"] * st["nz"]
     oracle.isoneutral_step(st)  # warm-up (page faults, thread pool)
-    n, t0 = 0, time.perf_counter()
-    times = []
+    n, t0, times = 0, time.perf_counter(), []
     while True:
         t1 = time.perf_counter()
         oracle.isoneutral_step(st)
@@ -139,58 +168,247 @@ def cpu_baseline(workload, seconds=12.0, threads=None):
         n += 1
         if time.perf_counter() - t0 > seconds or n >= 400:
             break
-    best = min(times)
     return {
-        "value": cells / best, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": f"{n} full steps of {name} {st['nx']}x{st['ny']}x{st['nz']} ({cells} cells), best of {n}, "
-                  f"C restatement of the reference NumPy path, OpenMP over x-planes",
+        "value": cells / min(times), "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{n} full steps of {name} {st['nx']}x{st['ny']}x{st['nz']} ({cells} cells"
+                  f"{', x-slab of the global grid' if kw else ''}), best of {n}; C/OpenMP restatement of the reference "
+                  f"NumPy path (oracle/), OpenMP over x-planes",
         "mean_value": cells * n / sum(times),
-    }, cells, min(times) * 1e3
+    }
 
 
-def workload_kwargs(args, world):
-    """Per-rank slab of the named workload (weak scaling: every rank gets the full named size)."""
-    return args.workload, {}
+def numpy_reference_baseline(name, steps, warmup, target_cells):
+    """The real reference (NumPy backend, baseline/_ref) on an x-slab sample of the workload; None if the
+    reference was not installed into baseline/_ref."""
+    from baseline import numpy_reference as nr
+    from veros_b200 import synthetic
+
+    if not nr.available():
+        return None
+    kw, nxs = sample_kwargs(name, target_cells)
+    st = synthetic.make_workload(name, **kw)
+    cells = st["nx"] * st["ny"] * st["nz"]
+    best, mean = nr.time_steps(st, steps, warmup)
+    return {
+        "value": cells / mean, "unit": UNIT, "cores": 1, "kind": "reference",
+        "sample": f"{steps} timed steps (+{warmup} warm-up) of the unmodified reference, NumPy backend (baseline/_ref: "
+                  f"isoneutral_diffusion_pre + isoneutral_diffusion(temp) + (salt), SciPy dgtsv column solve), on the x-slab "
+                  f"[0, {nxs}) of {name} = {st['nx']}x{st['ny']}x{st['nz']} ({cells} cells); single-threaded by construction "
+                  f"(NumPy ufuncs + LAPACK dgtsv); mean of the timed steps; JAX-CPU not measurable (jax is not installed)",
+        "best_value": cells / best, "ms_per_step": mean * 1e3, "cells": cells,
+    }
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
     if rank != 0:
         return
-    wl = workload_kwargs(args, 1)
-    base, cells, ms = cpu_baseline(wl, seconds=max(5.0, min(60.0, 4.0 * args.steps)))
+    name = args.workload
+    base = numpy_reference_baseline(name, args.steps, args.warmup, target_cells=1_000_000)
+    port = None
+    try:
+        pkw, _ = sample_kwargs(name, 8_000_000)
+        port = port_baseline(name, pkw, seconds=6.0)
+    except Exception as err:  # the port is context here, never the headline
+        port = {"error": str(err)}
+    if base is None:  # baseline/_ref absent: fall back to the port (kind says so)
+        base = port
+        ms = None
+    else:
+        ms = base["ms_per_step"]
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "note": "CPU oracle port of the reference NumPy path on host cores; "
-                   "the Python reference itself cannot travel to the GPU box"},
-        "cpu_baseline": base,
+        "scaling": "weak" if world == 1 else args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "note": "host cores only; each step is a bounded x-slab sample of the same workload "
+                   "the GPU arm runs (throughput per cell does not depend on the slab width)"},
+        "cpu_baseline": base, "oracle_port_all_cores": port,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
+# ---------------------------------------------------------------------------------------- helpers (GPU arm)
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank (and therefore its pinned staging buffers, first touch) to the NUMA node of its GPU: with 8
+    ranks staging through one socket the e2e leg collapses (round 1: 27 % weak efficiency)."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read())
+        if node < 0:
+            return None
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return node
+    except Exception:
+        return None
+    return None
+
+
+def timed(fn, n):
+    """Average device time of fn() in ms (CUDA events on the current stream)."""
+    import torch
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(n):
+        fn(k)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def side_measurements(dev, peak):
+    """The other single-GPU configs of BASELINE.json, each the fused step on its own synthetic state (not part of
+    `value`): bench_1M (configs[1]), global_4deg through a CUDA graph (configs[2], latency path), the ACC grid
+    (configs[0]) and the stand-alone column solve on the shapes of benchmarks/tdma_benchmark.py:30-39."""
+    import numpy as np
+    import torch
+
+    from veros_b200 import _lib, isoneutral, synthetic, utilities
+    from veros_b200.state import IsoState
+
+    out = {}
+    for name, reps, graph in (("bench_1M", 3, False), ("global_4deg", 4, True), ("acc", 4, True)):
+        st = synthetic.make_workload(name)
+        cells = st["nx"] * st["ny"] * st["nz"]
+        states = [IsoState.from_numpy(st, dev) for _ in range(reps)]
+        plans = [isoneutral.StepPlan(s) for s in states]
+        for p in plans:
+            p()
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        plans[0]()
+        launches = _lib.launch_count() - l0
+        ms = timed(lambda k: plans[k % reps](), 50)
+        rec = {"grid": f"{st['nx']}x{st['ny']}x{st['nz']}", "eq_of_state_type": int(st["eq_of_state_type"]),
+               "ms_per_step": ms, "value": cells / (ms * 1e-3), "kernel_launches_per_step": int(launches),
+               "step_roofline_frac": cells * algorithmic_bytes_per_cell(bool(st["enable_conserve_energy"])) / (ms * 1e-3) / 1e9 / peak}
+        if graph:
+            for p in plans:
+                p.capture()
+            msg = timed(lambda k: plans[k % reps](), 200)
+            rec.update(ms_per_step_cuda_graph=msg, value_cuda_graph=cells / (msg * 1e-3))
+        out[name] = rec
+        del states, plans
+        torch.cuda.empty_cache()
+    # stand-alone solve_implicit: random 70 x 60 x 50 systems as the reference's TDMA benchmark, and a 1 degree sized batch
+    rng = np.random.default_rng(17)
+    for label, (nx, ny, nz) in (("tdma_benchmark_70x60x50", (70, 60, 50)), ("global_1deg_364x164x115", (364, 164, 115))):
+        a, b, c, d = (torch.from_numpy(rng.standard_normal((nx, ny, nz))).to(dev) for _ in range(4))
+        kbot = rng.integers(0, nz, size=(nx, ny))
+        kk = np.arange(nz)[None, None, :]
+        water = torch.from_numpy(((kbot > 0)[..., None] & (kk >= (kbot - 1)[..., None]))).to(dev)
+        edge = torch.from_numpy(((kbot > 0)[..., None] & (kk == (kbot - 1)[..., None]))).to(dev)
+        for _ in range(3):
+            utilities.solve_implicit(a, b, c, d, water, edge)
+        ms = timed(lambda k: utilities.solve_implicit(a, b, c, d, water, edge), 30)
+        n = nx * ny * nz
+        out["solve_implicit_" + label] = {"ms": ms, "cells_per_s": n / (ms * 1e-3), "algorithmic_bytes_per_cell": SOLVE_BYTES_PER_CELL,
+                                          "achieved_gbs": n * SOLVE_BYTES_PER_CELL / (ms * 1e-3) / 1e9,
+                                          "frac": n * SOLVE_BYTES_PER_CELL / (ms * 1e-3) / 1e9 / peak,
+                                          "note": "native z-contiguous layout, dgtsv replay incl. pivoting, output allocation included"}
+    return out
+
+
+def seam_parity(args, name, nxl, rank, world, dev, cyclic, halo, overlap):
+    """One step of fresh slab states on all ranks (same stepper class as the timed run), then ranks 0 and 1
+    compare the planes either side of their common boundary -- the exchanged ghost planes included -- with a
+    single-GPU run of those planes (a 16-plane slab around the seam generated with the same x_offset mechanism).
+    Returns a dict on rank 0, None elsewhere."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from veros_b200 import decomp, isoneutral, synthetic
+    from veros_b200.state import IsoState
+
+    nxg = nxl * world
+    st = synthetic.make_workload(name, nx=nxl, x_offset=rank * nxl, nx_global=nxg)
+    lvl = int(st["taup1"])
+    gs = IsoState.from_numpy(st, dev)
+    if overlap:
+        decomp.OverlappedStepper(gs, cyclic=cyclic, halo=halo).step()
+    else:
+        isoneutral.isoneutral_step(gs)
+        make = decomp.PeerHaloExchange if halo == "peer" else decomp.TracerHaloExchange
+        make([gs.variables.temp, gs.variables.salt], level=lvl, cyclic=cyclic)()
+    torch.cuda.synchronize()
+    H = 8  # planes compared on each side
+    vs = gs.variables
+    names = ("temp", "salt", "dtemp_iso", "dsalt_iso", "K_33", "K_11")
+
+    def pick(t, sl):
+        t = t[sl]
+        return (t[..., lvl] if t.dim() == 4 else t).contiguous()
+
+    result = None
+    if rank == 1:
+        # west side of rank 1: ghost planes [0, 2) (filled by the exchange) + first H interior planes
+        buf = torch.stack([pick(getattr(vs, n), slice(0, 2 + H)) for n in names])
+        dist.send(buf, dst=0)
+    if rank == 0:
+        theirs = torch.empty((len(names), 2 + H) + tuple(vs.K_33.shape[1:]), dtype=torch.float64, device=dev)
+        dist.recv(theirs, src=1)
+        mine = torch.stack([pick(getattr(vs, n), slice(vs.K_33.shape[0] - 2 - H, vs.K_33.shape[0])) for n in names])
+        # single-GPU reference: interior planes [nxl - H, nxl + H) of the global grid as one small slab
+        seam = synthetic.make_workload(name, nx=2 * H, x_offset=nxl - H, nx_global=nxg)
+        ss = IsoState.from_numpy(seam, dev)
+        isoneutral.isoneutral_step(ss)
+        torch.cuda.synchronize()
+        ok, worst = True, {}
+        for q, n in enumerate(names):
+            ref = pick(getattr(ss.variables, n), slice(None))          # local planes 0 .. 2H+4 (ghosts + 2H interior)
+            # rank 0: its last H interior planes = seam interior [2, 2+H); its east ghosts = seam [2+H, 4+H) (tracers only)
+            a = torch.equal(mine[q][:H], ref[2:2 + H])
+            # rank 1: its first H interior planes = seam [2+H, 2+2H); its west ghosts = seam [H, 2+H) (tracers only)
+            b = torch.equal(theirs[q][2:], ref[2 + H:2 + 2 * H])
+            g = True
+            if n in ("temp", "salt"):
+                g = torch.equal(mine[q][H:], ref[2 + H:4 + H]) and torch.equal(theirs[q][:2], ref[H:2 + H])
+            ok = ok and a and b and g
+            worst[n] = bool(a and b and g)
+        result = {"bit_identical": bool(ok), "fields": worst,
+                  "checked": f"one step on fresh slabs; {H} interior planes either side of the rank 0 / rank 1 boundary and the "
+                             f"exchanged ghost planes of temp/salt[taup1] against a single-GPU step of global planes "
+                             f"[{nxl - H}, {nxl + H})"}
+    dist.barrier()
+    return result
+
+
+# ---------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--workload", default=None, help="default: global_1deg on one GPU, global_025deg on several")
     ap.add_argument("--replicas", type=int, default=0, help="state replicas rotated through (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-extra", action="store_true", help="skip the global_1deg side measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements under `also`")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (forced above 20 M cells per rank)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo exchange by stores into the neighbours' memory over NVLink (one kernel per rank, CUDA "
                          "IPC mappings) or by pack + NCCL send/recv + unpack")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: every rank gets a slab of the named size; strong: the named grid is split over the ranks")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong = the named grid is split over the ranks (default, BASELINE.json's 0.25 degree "
+                         "config); weak = every rank gets a slab of the named size")
     ap.add_argument("--profile", action="store_true",
                     help="only warm-up + timed steps + per-kernel pass (for ncu launch lists): no e2e, cpu or extra legs")
     ap.add_argument("--overlap", default="auto", choices=["auto", "on", "off"],
-                    help="N > 1: hide the halo exchange behind interior compute (auto: slabs of >= 3 M cells; "
-                         "below that the two extra boundary-strip passes cost more than the exchange)")
+                    help="N > 1: hide the halo exchange behind interior compute (auto: slabs of >= 3 M cells)")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3)
@@ -200,6 +418,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:
+        args.workload = default_workload(max(world, args.gpus))
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -216,6 +436,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -232,16 +453,20 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    name, kw = workload_kwargs(args, world)
-    if world > 1 and name != "bench_1M":
-        nxl = synthetic.WORKLOADS[name]["nx"]
-        if args.scaling == "strong":
-            if nxl % world:
-                raise SystemExit(f"--scaling strong: nx = {nxl} is not divisible by {world} ranks")
-            nxl //= world
-        kw = dict(nx=nxl, x_offset=rank * nxl, nx_global=nxl * world)
-    elif world > 1:
-        kw = dict(seed=17 + rank)
+    name, kw = args.workload, {}
+    scaling = "weak"
+    if world > 1:
+        scaling = args.scaling
+        if name == "bench_1M":
+            scaling = "weak"  # the random stress state has no global version: unrelated slabs, timing only
+            kw = dict(seed=17 + rank)
+        else:
+            nxl = synthetic.WORKLOADS[name]["nx"]
+            if scaling == "strong":
+                if nxl % world:
+                    raise SystemExit(f"--scaling strong: nx = {nxl} is not divisible by {world} ranks")
+                nxl //= world
+            kw = dict(nx=nxl, x_offset=rank * nxl, nx_global=nxl * world)  # one consistent global state
     st = synthetic.make_workload(name, **kw)
     nx, ny, nz = st["nx"], st["ny"], st["nz"]
     cells = nx * ny * nz
@@ -258,6 +483,7 @@ def main():
 
     plans = [isoneutral.StepPlan(s) for s in states]  # argument marshalling done once, as under XLA
     overlap = world > 1 and (args.overlap == "on" or (args.overlap == "auto" and cells >= 3_000_000))
+
     def build_exchange(halo):
         steppers_ = [decomp.OverlappedStepper(s, cyclic=cyclic, halo=halo) for s in states] if overlap else None
         make_exchange = decomp.PeerHaloExchange if halo == "peer" else decomp.TracerHaloExchange
@@ -272,12 +498,11 @@ def main():
         args.halo, halo_note = "nccl", f" (peer-memory mapping unavailable: {err})"
         steppers, exchanges = build_exchange("nccl")
 
-    def step(s):
-        q = states.index(s)
+    def step(q):
         if world == 1:
             plans[q]()
         elif steppers is not None:
-            steppers[q].step()  # boundary strips -> NCCL exchange || interior
+            steppers[q].step()  # boundary strips -> exchange || interior
         else:
             plans[q]()
             exchanges[q]()
@@ -286,7 +511,7 @@ def main():
     if rank == 0:
         sampler.start()
     for w in range(args.warmup):
-        step(states[w % replicas])
+        step(w % replicas)
     barrier()
     # ---- timed region: EXACTLY K steps -------------------------------------------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -294,7 +519,7 @@ def main():
     barrier()
     e0.record()
     for k in range(args.steps):
-        step(states[k % replicas])
+        step(k % replicas)
     e1.record()
     barrier()
     launches = _lib.launch_count() - launches0
@@ -319,12 +544,13 @@ def main():
         plans[k % replicas]()
         torch.cuda.synchronize()
     L.veros_b200_profile_events(None, 0)
+    k_pre = "iso_pre_kernel (slopes + tensor + fluxes)"
+    k_upd = "update_kernel (divergence + column solve + tendencies + dissipation)"
     kern_ms = {
         "setup (+eos5)": sum(r[0].elapsed_time(r[1]) for r in evs) / ksteps,
-        "iso_pre_kernel (slopes + tensor + fluxes)": sum(r[1].elapsed_time(r[2]) for r in evs) / ksteps,
-        "update_kernel (divergence + column solve + tendencies + dissipation)": sum(r[2].elapsed_time(r[3]) for r in evs) / ksteps,
+        k_pre: sum(r[1].elapsed_time(r[2]) for r in evs) / ksteps,
+        k_upd: sum(r[2].elapsed_time(r[3]) for r in evs) / ksteps,
     }
-    t_k1 = kern_ms["iso_pre_kernel (slopes + tensor + fluxes)"]
 
     # ---- the three stand-alone ops of the reference call surface, for context -----------------------------
     names = ("pre", "diffusion_temp", "diffusion_salt")
@@ -355,9 +581,15 @@ def main():
     for s_ in states:
         for k_, v_ in vmix_fields.items():
             setattr(s_.variables, k_, v_)
+    cyc_saved = [s_.settings.enable_cyclic_x for s_ in states]
+    for s_ in states:
         s_.settings.enable_cyclic_x = False  # kernel only: the exchange is timed with the step above
     vev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(ksteps)]
-    thermodynamics.vertmix_tempsalt(states[0])  # the reference-facing call once (allocates the tendencies)
+    if world == 1:
+        thermodynamics.vertmix_tempsalt(states[0])  # the reference-facing call once (allocates the tendencies)
+    else:
+        states[0].variables.dtemp_vmix = torch.empty((N_, M_, nz), dtype=torch.float64, device=dev)
+        states[0].variables.dsalt_vmix = torch.empty((N_, M_, nz), dtype=torch.float64, device=dev)
     for s_ in states[1:]:
         s_.variables.dtemp_vmix, s_.variables.dsalt_vmix = states[0].variables.dtemp_vmix, states[0].variables.dsalt_vmix
     vplans = [thermodynamics.VertmixPlan(s_) for s_ in states]
@@ -366,6 +598,8 @@ def main():
         vplans[k % replicas]()
         vev[k][1].record()
     torch.cuda.synchronize()
+    for s_, c_ in zip(states, cyc_saved):
+        s_.settings.enable_cyclic_x = c_
     vmix_ms = sum(e[0].elapsed_time(e[1]) for e in vev) / ksteps
     VMIX_BYTES = 56  # R temp,salt@taup1 16 + kappaH 8; W temp,salt 16 + dtemp_vmix,dsalt_vmix 16
 
@@ -374,8 +608,6 @@ def main():
     step_gbs = cells * step_bytes / (ms_step * 1e-3) / 1e9
     # dominant kernel of the step; algorithmic bytes: isoneutral_diffusion_pre 180 B/cell, the rest of the fused
     # step (276 or 244 B/cell) belongs to the update kernel
-    k_pre = "iso_pre_kernel (slopes + tensor + fluxes)"
-    k_upd = "update_kernel (divergence + column solve + tendencies + dissipation)"
     dom, dom_bytes, dom_key = (k_pre, PRE_BYTES_PER_CELL, "iso_pre_kernel") if kern_ms[k_pre] >= kern_ms[k_upd] else \
         (k_upd, step_bytes - PRE_BYTES_PER_CELL, "update_kernel")
     dom_gbs = cells * dom_bytes / (kern_ms[dom] * 1e-3) / 1e9
@@ -406,14 +638,22 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- end to end: host buffers in, host buffers out ----------------------------------------------
-    del states[1:]
+    # ---- multi-GPU: seam parity against a single-GPU run (fresh states, outside the timed region) --------
+    del states[1:], plans[1:]
+    steppers = exchanges = vplans = None
     torch.cuda.empty_cache()
+    parity = None
+    if world > 1 and name != "bench_1M":
+        parity = seam_parity(args, name, nx, rank, world, dev, cyclic, args.halo, overlap)
+
+    # ---- end to end: host buffers in, host buffers out ----------------------------------------------
     hs = None
     if args.no_e2e or cells > 20_000_000:
         clocks = sampler.stop() if rank == 0 else None
         e2e = None  # the pinned staging buffers of this leg would be tens of GB
     else:
+        del states[:], plans[:]
+        torch.cuda.empty_cache()
         hs = HostStepper(st, dev)
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(2):
@@ -426,43 +666,33 @@ def main():
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         clocks = sampler.stop() if rank == 0 else None  # sampled from warm-up to here (all under load)
         e2e = {"value": world * cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes,
-               "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps}
-
-    extra = None
-    if rank == 0 and world == 1 and not args.no_extra and name != "global_1deg":
-        # the north-star grid (1 degree, 6.6 M cells, EOS 5) measured the same way, for context
+               "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
+               "note": "HostStepper.step(): pinned host -> device copies of the step's inputs, the fused step, device -> host "
+                       "copies of all twelve outputs, slab-pipelined over three streams" +
+                       (f"; rank pinned to NUMA node {numa} of its GPU" if numa is not None else "")}
         del hs
         torch.cuda.empty_cache()
-        st1 = synthetic.make_workload("global_1deg")
-        c1 = st1["nx"] * st1["ny"] * st1["nz"]
-        ss = [IsoState.from_numpy(st1, dev) for _ in range(2)]
-        for w in range(3):
-            isoneutral.isoneutral_step(ss[w % 2])
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n1 = 20
-        a0.record()
-        for k in range(n1):
-            isoneutral.isoneutral_step(ss[k % 2])
-        a1.record()
-        torch.cuda.synchronize()
-        ms1 = a0.elapsed_time(a1) / n1
-        gbs1 = c1 * step_bytes / (ms1 * 1e-3) / 1e9
-        extra = {"workload": "global_1deg 360x160x115 analytic, EOS 5", "value": c1 / (ms1 * 1e-3), "ms_per_step": ms1,
-                 "step_roofline_frac": gbs1 / peak, "achieved_gbs": gbs1}
-        del ss
 
-    base = None
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = side_measurements(dev, peak)
+
+    base = ref_np = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        base, _, _ = cpu_baseline((name, kw))
+        base = port_baseline(name, kw)
+        try:
+            ref_np = numpy_reference_baseline(name, steps=3, warmup=1, target_cells=500_000)
+        except Exception as err:
+            ref_np = {"error": str(err)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": name, "nx": nx, "ny": ny, "nz": nz, "cells_per_gpu": cells,
+                "global_grid": f"{nx * world if (world > 1 and name != 'bench_1M') else nx}x{ny}x{nz}",
                 "eq_of_state_type": int(st["eq_of_state_type"]), "enable_conserve_energy": energy,
                 "parallelism": f"x-slabs x{world}" + (((" + ring halo exchange of temp/salt[taup1] by peer-memory stores over NVLink"
                                                         if args.halo == "peer" else " + NCCL ring halo exchange of temp/salt[taup1]") +
@@ -472,9 +702,11 @@ def main():
                        f"no replica is touched twice in a row") if replicas > 1 else
                       f"inputs larger than L2: one state of {state_bytes / 1e6:.0f} MB streamed per step",
             },
-            "roofline": roofline, "step_roofline": step_roofline, "next_ops": next_ops, "cpu_baseline": base, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "step_roofline": step_roofline, "next_ops": next_ops, "cpu_baseline": base,
+            "numpy_reference": ref_np, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if parity is not None:
+            line["multi_gpu_parity"] = parity
         if extra:
             line["also"] = extra
         emit(line)

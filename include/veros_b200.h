@@ -21,8 +21,9 @@
  * A trailing 5th argument (XlaCustomCallStatus*) passed by newer XLA versions is ignored.
  *
  * The ops only ENQUEUE work on `stream`: no allocation, no synchronisation, no retained state.
- * Errors (bad descriptor, failed launch) never throw or exit: they are printed to stderr and
- * latched; read them with veros_b200_last_error().  (The reference exits the process instead,
+ * Errors (bad descriptor, failed launch) never throw or exit: the first one since the latch was last cleared is
+ * printed to stderr and latched; read it with veros_b200_last_error().  A call stops enqueueing after its own
+ * first failure; an error latched by an earlier call does not turn later calls into no-ops.  (The reference exits the process instead,
  * cuda_tdma_kernels.cu:9-17,72-79.)
  *
  * Array conventions (veros/variables.py:75-162): C order, z fastest; N = nx+4, M = ny+4 include the
@@ -68,6 +69,10 @@ typedef struct VerosB200SolveDescriptor {
  * sub-slab, whose interior it is.  Used to pipeline host<->device copies and to overlap the halo exchange. */
 #define VEROS_B200_FLAG_NO_WEST_RING 2
 #define VEROS_B200_FLAG_NO_EAST_RING 4
+/* Tuning / test knobs of the slope kernel: force the one-launch (all faces) or the two-launch (east+north, then
+ * top faces) instantiation instead of choosing by grid size.  Results are identical either way. */
+#define VEROS_B200_FLAG_PRE_SINGLE 8
+#define VEROS_B200_FLAG_PRE_SPLIT 16
 
 /* Static (jit-constant) facts of the isoneutral ops: shapes and the settings of
  * veros/settings.py:24-91 that the path reads. */

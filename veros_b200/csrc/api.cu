@@ -15,16 +15,23 @@ static std::atomic<int> g_err{0};
 static std::atomic<unsigned long long> g_launches{0};
 static std::mutex g_err_mutex;
 static char g_err_text[256] = "";
+// Set by set_error on the calling thread: an entry point stops enqueueing after ITS OWN first failure, never because
+// of an error some other call or thread latched earlier (the latch itself is sticky until the host reads it).
+static thread_local bool t_call_failed = false;
 
 void set_error(int code, const char* what) {
+    t_call_failed = true;
     std::lock_guard<std::mutex> lock(g_err_mutex);
-    if (g_err.load() == 0) {
+    if (g_err.load() == 0) {  // first error since the host last cleared the latch: keep its text, print it once
         g_err.store(code);
         std::snprintf(g_err_text, sizeof(g_err_text), "%s (code %d%s%s)", what, code,
                       code < 100000 ? ": " : "", code < 100000 ? cudaGetErrorString((cudaError_t)code) : "");
+        std::fprintf(stderr, "veros_b200: %s\n", g_err_text);
     }
-    std::fprintf(stderr, "veros_b200: %s (code %d)\n", what, code);
 }
+
+bool call_failed() { return t_call_failed; }
+void begin_call() { t_call_failed = false; }
 
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n); }
 
@@ -89,6 +96,10 @@ void prof_mark(cudaStream_t s, int q) {
     if (g_prof_events && q < g_prof_n) cudaEventRecord(g_prof_events[q], s);
 }
 
+static int pre_variant(const VerosB200IsoDescriptor* d) {
+    return (d->flags & VEROS_B200_FLAG_PRE_SINGLE) ? 1 : (d->flags & VEROS_B200_FLAG_PRE_SPLIT) ? 2 : 0;
+}
+
 static size_t tabs_doubles(const VerosB200IsoDescriptor* d) {
     return (tables_doubles(d->nx_tot, d->ny_tot, d->nz) + 1) & ~(size_t)1;  // keep 16 B alignment behind it
 }
@@ -108,6 +119,7 @@ using namespace vb;
 extern "C" {
 
 void veros_b200_solve_implicit_f64(void* stream, void** B, const char* opaque, size_t len) {
+    begin_call();
     const auto* d = unpack<VerosB200SolveDescriptor>(opaque, len, "solve_implicit: bad descriptor");
     if (!d) return;
     if (d->num_systems < 0 || d->system_depth < 0) return set_error(VEROS_B200_ERR_BAD_ARGUMENT, "solve_implicit: negative size");
@@ -118,6 +130,7 @@ void veros_b200_solve_implicit_f64(void* stream, void** B, const char* opaque, s
 }
 
 void veros_b200_tdma_zmajor_f64(void* stream, void** B, const char* opaque, size_t len) {
+    begin_call();
     const auto* d = unpack<VerosB200TridiagDescriptor>(opaque, len, "tdma_zmajor_f64: bad descriptor");
     if (!d) return;
     launch_tdma_zmajor_f64((cudaStream_t)stream, d->num_systems, d->system_depth, (const double*)B[0], (const double*)B[1],
@@ -125,6 +138,7 @@ void veros_b200_tdma_zmajor_f64(void* stream, void** B, const char* opaque, size
 }
 
 void veros_b200_tdma_zmajor_f32(void* stream, void** B, const char* opaque, size_t len) {
+    begin_call();
     const auto* d = unpack<VerosB200TridiagDescriptor>(opaque, len, "tdma_zmajor_f32: bad descriptor");
     if (!d) return;
     launch_tdma_zmajor_f32((cudaStream_t)stream, d->num_systems, d->system_depth, (const float*)B[0], (const float*)B[1],
@@ -132,6 +146,7 @@ void veros_b200_tdma_zmajor_f32(void* stream, void** B, const char* opaque, size
 }
 
 void veros_b200_iso_pre_f64(void* stream, void** B, const char* opaque, size_t len) {
+    begin_call();
     const auto* d = unpack<VerosB200IsoDescriptor>(opaque, len, "iso_pre: bad descriptor");
     if (!valid_iso(d, "iso_pre: bad argument")) return;
     cudaStream_t s = (cudaStream_t)stream;
@@ -162,6 +177,7 @@ void veros_b200_iso_pre_f64(void* stream, void** B, const char* opaque, size_t l
     a.drdS = a.drdT + n3;
     a.with_flux = 0;
     a.with_stage = 0;
+    a.variant = pre_variant(d);
     a.stage[0] = a.stage[1] = nullptr;
     a.stage_src[0] = a.stage_src[1] = nullptr;
     for (int t = 0; t < 2; ++t)
@@ -174,6 +190,7 @@ void veros_b200_iso_pre_f64(void* stream, void** B, const char* opaque, size_t l
 }
 
 void veros_b200_iso_diffusion_f64(void* stream, void** B, const char* opaque, size_t len) {
+    begin_call();
     const auto* d = unpack<VerosB200IsoDescriptor>(opaque, len, "iso_diffusion: bad descriptor");
     if (!valid_iso(d, "iso_diffusion: bad argument")) return;
     cudaStream_t s = (cudaStream_t)stream;
@@ -215,11 +232,12 @@ void veros_b200_iso_diffusion_f64(void* stream, void** B, const char* opaque, si
     double* ws = (double*)B[28];
     a.tables = ws + diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 1);
     launch_setup_tables(s, a.g, d->dt_tracer, a.tables);
-    if (veros_b200_last_error()) return;
+    if (call_failed()) return;
     launch_iso_diffusion_ws(s, a, ws);
 }
 
 void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t len) {
+    begin_call();
     const auto* d = unpack<VerosB200IsoDescriptor>(opaque, len, "iso_step: bad descriptor");
     if (!valid_iso(d, "iso_step: bad argument")) return;
     cudaStream_t s = (cudaStream_t)stream;
@@ -255,8 +273,9 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     p.drdS = p.drdT + n3;
     prof_mark(s, 0);
     launch_setup_tables(s, p.g, d->dt_tracer, p.tables);
-    if (veros_b200_last_error()) return;
+    if (call_failed()) return;
     p.with_flux = 1;
+    p.variant = pre_variant(d);
     for (int t = 0; t < 2; ++t)
         for (int q = 0; q < 3; ++q) p.flux[t][q] = ws + (size_t)(3 * t + q) * n3;
     p.with_stage = energy ? 1 : 0;
@@ -269,7 +288,7 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     p.iso_slopec = d->iso_slopec;
     p.iso_dslope = d->iso_dslope;
     launch_iso_pre(s, p, /*profile=*/true);
-    if (veros_b200_last_error()) return;
+    if (call_failed()) return;
 
     DiffArgs a;
     a.g = p.g;
@@ -310,6 +329,7 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
 }
 
 void veros_b200_vertmix_tempsalt_f64(void* stream, void** B, const char* opaque, size_t len) {
+    begin_call();
     const auto* d = unpack<VerosB200VmixDescriptor>(opaque, len, "vertmix_tempsalt: bad descriptor");
     if (!d) return;
     if (d->nx_tot < 0 || d->ny_tot < 0 || d->nz < 0 || !(d->dt_tracer > 0.0))

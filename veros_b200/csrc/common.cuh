@@ -4,6 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "../../include/veros_b200.h"
 
 namespace vb {
@@ -12,6 +16,26 @@ namespace vb {
 void set_error(int code, const char* what);
 void count_launch(int n = 1);
 bool check_launch(const char* what);  // cudaPeekAtLastError -> latch; true if ok
+bool call_failed();                   // an error was latched by the current entry-point call on this thread
+void begin_call();
+constexpr int kMaxDevices = 64;        // per-device caches (occupancy, function attributes) are indexed by device
+// Opt a kernel in to more than 48 KB of dynamic shared memory on the CURRENT device.  The attribute is per
+// (kernel, device), so the "already done" record is keyed by both (a process may drive several GPUs); after the
+// first call for a pair this is a short table lookup, which also keeps CUDA-graph capture free of attribute calls.
+inline void allow_big_smem_fn(const void* fn, int bytes) {
+    struct Done { const void* fn; int dev, bytes; };
+    static std::mutex mu;
+    static std::vector<Done> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Done& d : done)
+        if (d.fn == fn && d.dev == dev && d.bytes >= bytes) return;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    done.push_back(Done{fn, dev, bytes});
+}
+template <typename K>
+inline void allow_big_smem(K kernel, int bytes) { allow_big_smem_fn(reinterpret_cast<const void*>(kernel), bytes); }
 
 // ---- pointers of one isoneutral problem (all device memory) -------------------------------------
 struct Grid {
@@ -40,6 +64,7 @@ struct PreArgs {
     const double* stage_src[2];
     double* stage[2];
     int with_stage;
+    int variant;  // 0: by size, 1: one launch for all faces, 2: east+north / top launches (VEROS_B200_FLAG_PRE_*)
     int eos;
     double K_iso_steep, iso_slopec, iso_dslope;
 };

@@ -490,11 +490,7 @@ void launch_update(cudaStream_t s, const DiffArgs& a, const Scratch& f) {
     }
     const size_t smem = lev_bytes + 8 * ((size_t)(3 + NTR) * cols * pitch + (size_t)cols * 4 + (cols + 1) / 2 + 1) + 16;
     auto kern = update_kernel<NTR, SKEW, ENERGY>;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured = true;
-    }
+    allow_big_smem(kern, 200 * 1024);  // per device, not per process
     dim3 grid((M - 2 + cols - 1) / cols, N - 2);
     kern<<<grid, kUpdBlock, smem, s>>>(a, f, cols, pitch, fac_diss, gr);
     count_launch();

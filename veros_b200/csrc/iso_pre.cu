@@ -26,6 +26,7 @@
 // bit (NumPy's SIMD tanh is not reproducible either).  The FLUXES are strict: given the stored Ai_*
 // and K_* they are bit-identical to the reference's expressions (flux_device.cuh).
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -561,28 +562,39 @@ iso_pre_kernel(const PreArgs a) {
 }
 
 // One resident wave: CTAs per SM of this instantiation x SMs, never more CTAs than chunks.
+// Cached per (instantiation, device): the answer depends on the SM count of the device that is current.
 template <typename K>
 static unsigned resident_grid(K kernel, int total_chunks) {
-    int per_sm = 0, dev = 0, sms = 148;
+    static std::atomic<unsigned> cache[kMaxDevices];
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPreBlock, 0) != cudaSuccess || per_sm < 1) per_sm = 3;
-    return (unsigned)std::max(1, std::min(total_chunks, per_sm * sms));
+    unsigned full = (dev >= 0 && dev < kMaxDevices) ? cache[dev].load(std::memory_order_relaxed) : 0u;
+    if (full == 0u) {
+        int per_sm = 0, sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPreBlock, 0) != cudaSuccess || per_sm < 1) per_sm = 3;
+        full = (unsigned)(per_sm * sms);
+        if (dev >= 0 && dev < kMaxDevices) cache[dev].store(full, std::memory_order_relaxed);
+    }
+    return (unsigned)std::max(1, std::min(total_chunks, (int)full));
 }
 
 template <int EOS, bool FLUX>
 static void launch_pre_variant(cudaStream_t s, const PreArgs& a, int total_chunks) {
-    static const bool force_single = getenv("VEROS_B200_PRE_SINGLE") != nullptr;  // tuning knob
     // measured (profiles/): the split is +3 % on the 1 degree grid, neutral at 1 M cells, and costs one
-    // launch, which small grids cannot afford
-    const bool single = force_single || (size_t)a.g.N * a.g.M * a.g.nz < 500000;
+    // launch, which small grids cannot afford.  VEROS_B200_FLAG_PRE_SINGLE / _PRE_SPLIT (descriptor) or the
+    // environment variables VEROS_B200_PRE_SINGLE / VEROS_B200_PRE_SPLIT force one of the two, so that the
+    // parity tests reach both instantiations on every fixture.
+    bool single = (size_t)a.g.N * a.g.M * a.g.nz < 500000;
+    if (a.variant == 1 || getenv("VEROS_B200_PRE_SINGLE")) single = true;
+    if (a.variant == 2 || getenv("VEROS_B200_PRE_SPLIT")) single = false;
     if (single) {
-        static const unsigned full = resident_grid(iso_pre_kernel<EOS, FLUX, 7>, 1 << 30);
+        const unsigned full = resident_grid(iso_pre_kernel<EOS, FLUX, 7>, 1 << 30);
         iso_pre_kernel<EOS, FLUX, 7><<<std::min(full, (unsigned)total_chunks), kPreBlock, 0, s>>>(a);
         count_launch();
     } else {
-        static const unsigned full3 = resident_grid(iso_pre_kernel<EOS, FLUX, 3>, 1 << 30);
-        static const unsigned full4 = resident_grid(iso_pre_kernel<EOS, FLUX, 4>, 1 << 30);
+        const unsigned full3 = resident_grid(iso_pre_kernel<EOS, FLUX, 3>, 1 << 30);
+        const unsigned full4 = resident_grid(iso_pre_kernel<EOS, FLUX, 4>, 1 << 30);
         iso_pre_kernel<EOS, FLUX, 3><<<std::min(full3, (unsigned)total_chunks), kPreBlock, 0, s>>>(a);
         iso_pre_kernel<EOS, FLUX, 4><<<std::min(full4, (unsigned)total_chunks), kPreBlock, 0, s>>>(a);
         count_launch(2);

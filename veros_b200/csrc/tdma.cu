@@ -77,11 +77,7 @@ void launch_solve_implicit(cudaStream_t s, int ncol, int nz, const double* a, co
     const int want_tiles = 2 * 148;
     if ((ncol + cols - 1) / cols < want_tiles) cols = max(1, (ncol + want_tiles - 1) / want_tiles);
     const size_t smem = (size_t)4 * 8 * cols * pitch + sizeof(int) * cols + 24;  // + the two guard elements
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(solve_implicit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured = true;
-    }
+    allow_big_smem(solve_implicit_kernel, 200 * 1024);  // per device, not per process
     const int grid = (ncol + cols - 1) / cols;
     solve_implicit_kernel<<<grid, 256, smem, s>>>(ncol, nz, cols, pitch, a, b, c, d, water, edge, b_edge, d_edge, out);
     count_launch();

@@ -130,11 +130,7 @@ void launch_vertmix(cudaStream_t s, const VmixArgs& a) {
         cols = max(1, (M + per_row - 1) / per_row);
     }
     const size_t smem = (size_t)nz * (sizeof(Divisor) + 8) + 8 * ((size_t)5 * cols * pitch + (cols + 1) / 2 + 1);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(vertmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured = true;
-    }
+    allow_big_smem(vertmix_kernel, 200 * 1024);  // per device, not per process
     dim3 grid((M + cols - 1) / cols, N);
     vertmix_kernel<<<grid, kVmixBlock, smem, s>>>(a, cols, pitch);
     count_launch();

@@ -103,22 +103,33 @@ class TracerHaloExchange:
         self._check = _lib.check_error
         self._vp = ctypes.c_void_p
 
-    def _launch(self, mode, west, east):
+    def _launch(self, mode, west, east, level):
         s = torch.cuda.current_stream(self.fields[0].device).cuda_stream
-        self._fn(self._vp(s), mode, self._ptrs, len(self.fields), self.N, self.M, self.nz, self.nlev, self.level,
+        self._fn(self._vp(s), mode, self._ptrs, len(self.fields), self.N, self.M, self.nz, self.nlev, level,
                  self._vp(west.data_ptr()) if west is not None else None,
                  self._vp(east.data_ptr()) if east is not None else None)
 
-    def __call__(self):
+    def _level(self, level):
+        """Time level of this exchange: the model rotates tau/taup1 every step (veros/core/numerics.py), so the
+        caller passes the current taup1 per call; the constructor's value is only the default."""
+        if self.nlev == 1:
+            return 0
+        level = self.level if level is None else int(level)
+        if not 0 <= level < self.nlev:
+            raise ValueError(f"time level {level} outside [0, {self.nlev})")
+        return level
+
+    def __call__(self, level=None):
+        level = self._level(level)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         west, east = neighbours(rank, world, self.cyclic)
         if world == 1:
             if self.cyclic:  # wrap around locally: east edge -> west ghosts, west edge -> east ghosts
-                self._launch(0, self.send_w, self.send_e)
-                self._launch(1, self.send_e, self.send_w)
+                self._launch(0, self.send_w, self.send_e, level)
+                self._launch(1, self.send_e, self.send_w, level)
             return
-        self._launch(0, self.send_w if west is not None else None, self.send_e if east is not None else None)
+        self._launch(0, self.send_w if west is not None else None, self.send_e if east is not None else None, level)
         ops = []  # posting order: see exchange_halos_x
         if east is not None:
             ops.append(dist.P2POp(dist.isend, self.send_e, east, self.group))
@@ -130,7 +141,7 @@ class TracerHaloExchange:
             ops.append(dist.P2POp(dist.irecv, self.recv_e, east, self.group))
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-        self._launch(1, self.recv_w if west is not None else None, self.recv_e if east is not None else None)
+        self._launch(1, self.recv_w if west is not None else None, self.recv_e if east is not None else None, level)
         self._check("halo exchange")
 
 
@@ -239,13 +250,20 @@ class PeerHaloExchange:
         if world > 1:
             dist.barrier(group=group)  # nobody starts exchanging before every mapping exists
 
-    def __call__(self):
+    def __call__(self, level=None):
+        """`level`: the time level to exchange now (default: the constructor's); all ranks pass the same value."""
+        if self.nlev == 1:
+            level = 0
+        else:
+            level = self.level if level is None else int(level)
+            if not 0 <= level < self.nlev:
+                raise ValueError(f"time level {level} outside [0, {self.nlev})")
         if self._west is None and self._east is None:
             return
         self._seq += 1
         s = torch.cuda.current_stream(self.fields[0].device).cuda_stream
         self._fn(self._vp(s), self._seq, self._mine, self._west, self._east, len(self.fields), self.N, self._n_west,
-                 self.M, self.nz, self.nlev, self.level, self._vp(self.flags.data_ptr()),
+                 self.M, self.nz, self.nlev, level, self._vp(self.flags.data_ptr()),
                  self._vp(self._west_flags) if self._west_flags is not None else None,
                  self._vp(self._east_flags) if self._east_flags is not None else None,
                  self._vp(self.counter.data_ptr()))
@@ -293,6 +311,8 @@ class OverlappedStepper:
             self.ev_strips.record(self.s_strip)
         with torch.cuda.stream(self.s_comm):
             self.s_comm.wait_event(self.ev_strips)
-            self.exchange()
+            # the level the step just wrote: taup1 as of NOW (IsoState.advance_time keeps the host copy in step
+            # with the device scalar the kernels read), not as of construction
+            self.exchange(level=vs.taup1_host)
         self.plans[2]()
         cur.wait_stream(self.s_comm)

@@ -25,7 +25,7 @@ def _descriptor(state, flags=0):
     st = state.settings
     return _lib.IsoDescriptor(
         nx_tot=st.nx + 4, ny_tot=st.ny + 4, nz=st.nz, eq_of_state_type=st.eq_of_state_type,
-        enable_conserve_energy=int(st.enable_conserve_energy), flags=flags | getattr(state, "ring_flags", 0),
+        enable_conserve_energy=int(st.enable_conserve_energy), flags=flags | getattr(state, "ring_flags", 0) | getattr(state, "tuning_flags", 0),
         K_iso_steep=st.K_iso_steep, iso_slopec=st.iso_slopec, iso_dslope=st.iso_dslope,
         dt_tracer=st.dt_tracer, grav=st.grav, rho_0=st.rho_0)
 

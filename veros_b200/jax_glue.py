@@ -105,6 +105,11 @@ def _make_primitive(name, n_inout, inout_first, has_workspace, workspace_bytes, 
     prim.multiple_results = True
 
     def abstract_eval(*avals, descriptor):
+        # the kernels are float64 / uint8 / int32 only: anything else would be read with the wrong element
+        # size (the reference supports float32 runs, veros/runtime.py:93; this library does not)
+        for a in avals:
+            if np.dtype(a.dtype) not in (np.dtype(np.float64), np.dtype(np.uint8), np.dtype(np.int32)):
+                raise TypeError(f"{name}: operand dtype {a.dtype} is not supported (float64 / uint8 / int32 only)")
         n = len(avals)
         idx = range(n_inout) if inout_first else range(n - n_inout, n)
         outs = [ShapedArray(avals[i].shape, avals[i].dtype) for i in idx]
@@ -219,6 +224,8 @@ def make_replacements():
             raise ValueError("all inputs must have identical shape")
         if not a.dtype == b.dtype == c.dtype == d.dtype:
             raise ValueError("all inputs must have the same dtype")
+        if a.dtype != jnp.float64:  # same error as veros_b200/utilities.py and tdma_.py:56-57
+            raise TypeError(f"solve_tridiagonal only supports float64 arrays, got: {a.dtype}")
         nz = a.shape[-1]
         flags = (_lib.HAS_B_EDGE if b_edge is not None else 0) | (_lib.HAS_D_EDGE if d_edge is not None else 0)
         desc = _lib.SolveDescriptor(num_systems=a.size // nz, system_depth=nz, flags=flags, reserved=0)
@@ -255,6 +262,8 @@ def install():
 
     if rs.backend != "jax" or rs.device != "gpu":
         raise RuntimeError("veros_b200 has no CPU path: it needs backend='jax' and device='gpu'")
+    if rs.float_type != "float64":
+        raise RuntimeError(f"veros_b200 kernels are float64 only (runtime_settings.float_type = {rs.float_type!r})")
     _lib.lib()
     register()
     import veros.core.isoneutral as iso_pkg

@@ -54,6 +54,7 @@ class IsoState:
         self._workspace = None
         self._dummy = torch.zeros(8, dtype=torch.float64, device=device)
         self.ring_flags = 0  # VEROS_B200_FLAG_NO_WEST_RING / _NO_EAST_RING for x-sub-slab views
+        self.tuning_flags = 0  # VEROS_B200_FLAG_PRE_SINGLE / _PRE_SPLIT ...: kernel-variant knobs (tests, tuning)
 
     # ---- construction --------------------------------------------------------------------------
     @classmethod
@@ -126,6 +127,20 @@ class IsoState:
         if not 1 <= st.eq_of_state_type <= 5:
             raise ValueError("unknown equation of state")
 
+    # ---- time stepping ---------------------------------------------------------------------------
+    def advance_time(self):
+        """Rotate the time-level indices like the end of a model step (veros/veros.py: taum1, tau, taup1 =
+        tau, taup1, taum1): the device scalars the kernels read and the host copies the plumbing uses (halo
+        exchange level) change TOGETHER.  Sub-slab views share both with their parent."""
+        vs = self.variables
+        tau, taup1 = int(vs.tau_host), int(vs.taup1_host)
+        taum1 = 3 - tau - taup1
+        vs.tau_host, vs.taup1_host = taup1, taum1
+        vs.tau.fill_(taup1)
+        vs.taup1.fill_(taum1)
+        for sub in getattr(self, "_views", ()):
+            sub.variables.tau_host, sub.variables.taup1_host = taup1, taum1
+
     # ---- helpers --------------------------------------------------------------------------------
     def to_numpy(self, names=None):
         vs = self.variables
@@ -156,8 +171,12 @@ class IsoState:
         settings.nx = (i1 - i0) - 4
         sub = IsoState(vs, settings, self.device)
         sub._dummy = self._dummy
+        sub.tuning_flags = self.tuning_flags
         sub.ring_flags = (0 if i0 == 0 else _lib.FLAG_NO_WEST_RING) | (0 if i1 == N else _lib.FLAG_NO_EAST_RING)
         sub._parent = self
+        if not hasattr(self, "_views"):
+            self._views = []
+        self._views.append(sub)  # advance_time() keeps the views' host-side time levels in step
         return sub
 
     def workspace(self, nbytes):
