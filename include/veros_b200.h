@@ -73,6 +73,10 @@ typedef struct VerosB200SolveDescriptor {
  * top faces) instantiation instead of choosing by grid size.  Results are identical either way. */
 #define VEROS_B200_FLAG_PRE_SINGLE 8
 #define VEROS_B200_FLAG_PRE_SPLIT 16
+/* iso_step: run the step as separate launches (table setup, TEOS-10 pass, slope + flux kernel(s), update kernel)
+ * instead of the one persistent kernel that is the default.  Same results bit for bit; kept for A/B measurements and
+ * so that the parity tests cover the kernels the stand-alone ops use. */
+#define VEROS_B200_FLAG_STEP_CLASSIC 32
 
 /* Static (jit-constant) facts of the isoneutral ops: shapes and the settings of
  * veros/settings.py:24-91 that the path reads. */

@@ -68,6 +68,7 @@ HAS_B_EDGE, HAS_D_EDGE = 1, 2
 FLAG_SKEW = 1
 FLAG_NO_WEST_RING, FLAG_NO_EAST_RING = 2, 4
 FLAG_PRE_SINGLE, FLAG_PRE_SPLIT = 8, 16
+FLAG_STEP_CLASSIC = 32
 
 _lib = None
 

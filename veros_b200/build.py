@@ -21,6 +21,7 @@ SOURCES = {
     "tdma.cu": ["-fmad=false"],
     "iso_pre.cu": [],
     "iso_diffusion.cu": [],
+    "iso_mega.cu": [],
     "halo.cu": [],
     "vertmix.cu": [],
 }

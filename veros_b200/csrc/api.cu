@@ -3,6 +3,7 @@
 // kernels on the caller's stream.  Nothing here allocates, synchronises or throws.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -265,30 +266,15 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     p.K_11 = (double*)B[40];
     p.K_22 = (double*)B[41];
     p.K_33 = (double*)B[42];
-    double* stage = ws + diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 2);  // behind the flux/scratch arrays
-    p.tables = stage + step_stage_doubles(d);
-    p.tables_ready = 1;
+    const bool classic = (d->flags & VEROS_B200_FLAG_STEP_CLASSIC) != 0 || getenv("VEROS_B200_STEP_CLASSIC") != nullptr;
     p.dt_tracer = d->dt_tracer;
-    p.drdT = p.tables + tabs_doubles(d);
-    p.drdS = p.drdT + n3;
-    prof_mark(s, 0);
-    launch_setup_tables(s, p.g, d->dt_tracer, p.tables);
-    if (call_failed()) return;
-    p.with_flux = 1;
-    p.variant = pre_variant(d);
-    for (int t = 0; t < 2; ++t)
-        for (int q = 0; q < 3; ++q) p.flux[t][q] = ws + (size_t)(3 * t + q) * n3;
-    p.with_stage = energy ? 1 : 0;
-    p.stage_src[0] = (const double*)B[29];
-    p.stage_src[1] = (const double*)B[30];
-    p.stage[0] = energy ? stage : nullptr;
-    p.stage[1] = energy ? stage + n3 : nullptr;
     p.eos = d->eq_of_state_type;
     p.K_iso_steep = d->K_iso_steep;
     p.iso_slopec = d->iso_slopec;
     p.iso_dslope = d->iso_dslope;
-    launch_iso_pre(s, p, /*profile=*/true);
-    if (call_failed()) return;
+    p.stage_src[0] = (const double*)B[29];
+    p.stage_src[1] = (const double*)B[30];
+    p.variant = pre_variant(d);
 
     DiffArgs a;
     a.g = p.g;
@@ -317,13 +303,49 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     a.energy = energy ? 1 : 0;
     a.skip_west_ring = (d->flags & VEROS_B200_FLAG_NO_WEST_RING) ? 1 : 0;
     a.skip_east_ring = (d->flags & VEROS_B200_FLAG_NO_EAST_RING) ? 1 : 0;
+    a.dt_tracer = d->dt_tracer;
+    a.grav = d->grav;
+    a.rho_0 = d->rho_0;
+
+    if (!classic) {
+        // ---- the fused persistent kernel (iso_mega.cu): tables | queue + counters | scratch ring --------------------
+        p.tables = ws;
+        p.tables_ready = 1;
+        unsigned int* sync = reinterpret_cast<unsigned int*>(ws + tabs_doubles(d));
+        double* ring = ws + tabs_doubles(d) + mega_sync_doubles(d->nx_tot);
+        a.tables = p.tables;
+        a.fluxes_ready = 1;
+        prof_mark(s, 0);
+        launch_setup_tables(s, p.g, d->dt_tracer, p.tables, sync, 4 * d->nx_tot + 2);
+        if (call_failed()) return;
+        prof_mark(s, 1);
+        launch_iso_mega(s, p, a, ring, sync);
+        prof_mark(s, 2);
+        prof_mark(s, 3);
+        return;
+    }
+
+    // ---- separate launches: setup, (TEOS-10), slope + flux kernel(s), update kernel --------------------------------
+    double* stage = ws + diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 2);  // behind the flux/scratch arrays
+    p.tables = stage + step_stage_doubles(d);
+    p.tables_ready = 1;
+    p.drdT = p.tables + tabs_doubles(d);
+    p.drdS = p.drdT + n3;
+    prof_mark(s, 0);
+    launch_setup_tables(s, p.g, d->dt_tracer, p.tables);
+    if (call_failed()) return;
+    p.with_flux = 1;
+    for (int t = 0; t < 2; ++t)
+        for (int q = 0; q < 3; ++q) p.flux[t][q] = ws + (size_t)(3 * t + q) * n3;
+    p.with_stage = energy ? 1 : 0;
+    p.stage[0] = energy ? stage : nullptr;
+    p.stage[1] = energy ? stage + n3 : nullptr;
+    launch_iso_pre(s, p, /*profile=*/true);
+    if (call_failed()) return;
     a.fluxes_ready = 1;
     a.stage_x[0] = p.stage[0];
     a.stage_x[1] = p.stage[1];
     a.tables = p.tables;
-    a.dt_tracer = d->dt_tracer;
-    a.grav = d->grav;
-    a.rho_0 = d->rho_0;
     launch_iso_diffusion_ws(s, a, ws);
     prof_mark(s, 3);
 }
@@ -376,7 +398,11 @@ size_t veros_b200_iso_diffusion_workspace_bytes(const char* opaque, size_t len) 
 size_t veros_b200_iso_step_workspace_bytes(const char* opaque, size_t len) {
     const auto* d = unpack<VerosB200IsoDescriptor>(opaque, len, "iso_step_workspace_bytes: bad descriptor");
     if (!d) return 0;
-    return 8 * (pre_ws_doubles(d) + diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 2) + step_stage_doubles(d));
+    // enough for either implementation of the step (the descriptor flags choose at call time)
+    const size_t classic = pre_ws_doubles(d) + diffusion_workspace_doubles(d->nx_tot, d->ny_tot, d->nz, 2) + step_stage_doubles(d);
+    const size_t fused = tabs_doubles(d) + mega_sync_doubles(d->nx_tot) +
+                         mega_ring_doubles(d->nx_tot, d->ny_tot, d->nz, d->eq_of_state_type, d->enable_conserve_energy != 0);
+    return 8 * (classic > fused ? classic : fused);
 }
 
 int veros_b200_last_error(void) { return g_err.load(); }

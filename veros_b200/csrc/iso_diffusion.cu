@@ -163,280 +163,14 @@ flux_kernel(const DiffArgs a, const int t, double* __restrict__ flux_east, doubl
 //   phase D  per cell: implicit result, tendency, dissipation (the T-point dissipation of levels
 //            k and k+1 is recomputed from the fluxes instead of being staged)
 // ------------------------------------------------------------------------------------------------
-struct Scratch {
-    const double *fe[2], *fn[2], *ft[2];
-    double* diss[2];  // T-point dissipation of each tracer (ENERGY only)
-};
+}  // namespace
+}  // namespace vb
 
-constexpr int kUpdBlock = 128;
+#include "iso_update_phases.cuh"
 
-// ---- pieces of the update shared by the plain and the pipelined kernel ---------------------------------
-struct LevelTabs {        // per level, once per CTA
-    Divisor* ddzt;        // dzt[k]
-    Divisor* ddzw;        // dzw[k]
-    double* dt_dzw;       // dt_tracer / dzw[k]
-};
-struct TileBuf {          // one tile of whole columns in shared memory
-    double *L, *D, *U, *R[2];
-    Divisor *dcdxt, *dcdyt;  // cost[j]*dxt[i], cost[j]*dyt[j] per column
-    int* ksv;                // kbot - 1 per column
-};
-struct TileGeom {
-    int i, j0, ncols, ncells;
-    size_t base;
-    bool i_int;
-};
-struct UpdConst {
-    int N, M, nz, pitch, tau, taup1;
-    size_t plane;
-    double dt, fac_diss, gr;
-    Divisor ddt;
-};
-
-__device__ __forceinline__ TileBuf tile_buf_at(double* p, int cols, int pitch, int ntr) {
-    TileBuf b;
-    const int tile = cols * pitch;
-    b.L = p;
-    b.D = b.L + tile;
-    b.U = b.D + tile;
-    b.R[0] = b.U + tile;
-    b.R[1] = b.R[0] + (ntr > 1 ? tile : 0);
-    b.dcdxt = reinterpret_cast<Divisor*>(b.R[0] + (size_t)ntr * tile);
-    b.dcdyt = b.dcdxt + cols;
-    b.ksv = reinterpret_cast<int*>(b.dcdyt + cols);
-    return b;
-}
-
-__device__ __forceinline__ TileGeom tile_geom(const UpdConst& u, int i, int j0, int cols) {
-    TileGeom g;
-    g.i = i;
-    g.j0 = j0;
-    g.ncols = min(cols, (u.M - 1) - j0);
-    g.ncells = g.ncols * u.nz;
-    g.base = (size_t)i * u.plane + (size_t)j0 * u.nz;
-    g.i_int = (i >= 2 && i < u.N - 2);
-    return g;
-}
-
-__device__ __forceinline__ void fill_level_tabs(const DiffArgs& a, const LevelTabs& lv, int nz, double dt, int tid, int nthr) {
-    for (int k = tid; k < nz; k += nthr) {
-        lv.ddzt[k] = make_divisor(a.g.dzt[k]);
-        lv.ddzw[k] = make_divisor(a.g.dzw[k]);
-        lv.dt_dzw[k] = strict::div(dt, a.g.dzw[k]);
-    }
-}
-
-__device__ __forceinline__ void fill_tile_tabs(const DiffArgs& a, const UpdConst& u, const TileBuf& b, const TileGeom& g,
-                                               int tid, int nthr) {
-    for (int q = tid; q < g.ncols; q += nthr) {
-        const int j = g.j0 + q;
-        b.dcdxt[q] = make_divisor(mul(a.g.cost[j], a.g.dxt[g.i]));
-        b.dcdyt[q] = make_divisor(mul(a.g.cost[j], a.g.dyt[j]));
-        b.ksv[q] = a.kbot[g.i * u.M + j] - 1;
-    }
-}
-
-// phase B: explicit flux divergence, tracer + tendency update, right-hand sides, matrix, T-point dissipation
-template <int NTR, bool SKEW, bool ENERGY>
-__device__ __forceinline__ void phase_b(const DiffArgs& a, const Scratch& f, const UpdConst& u, const LevelTabs& lv,
-                                        const TileBuf& b, const TileGeom& g, int tid, int nthr) {
-    const int N = u.N, M = u.M, nz = u.nz, pitch = u.pitch, tau = u.tau, taup1 = u.taup1;
-    const size_t plane = u.plane;
-    const double dt = u.dt, fac_diss = u.fac_diss;
-    (void)N;
-    // ---- phase B --------------------------------------------------------------------------------
-    // Every global load of a (cell, tracer) pair is issued before the first dependent store: the
-    // compiler must keep loads behind earlier stores that might alias, so interleaving them would
-    // serialise four memory round trips per cell.
-    for (int idx = tid; idx < g.ncells; idx += nthr) {
-        const int q = idx / nz, k = idx - q * nz;
-        const int j = g.j0 + q;
-        const bool interior = g.i_int && j >= 2 && j < M - 2;
-        if (!interior && !ENERGY) continue;
-        const size_t c = g.base + idx;
-        const int s = q * pitch + k;
-        const double mT = interior ? (double)a.maskT[c] : 0.0;
-        double k33 = 0.0, k33m = 0.0;
-        if (!SKEW && interior) {
-            k33 = (k < nz - 1) ? __ldg(a.K_33 + c) : 0.0;
-            k33m = (k > 0) ? __ldg(a.K_33 + c - 1) : 0.0;
-        }
-#pragma unroll
-        for (int t = 0; t < NTR; ++t) {
-            // loads
-            const double fe_c = __ldg(f.fe[t] + c), fe_w = __ldg(f.fe[t] + c - plane);
-            const double fn_c = __ldg(f.fn[t] + c), fn_s = __ldg(f.fn[t] + c - nz);
-            double ft_c = 0.0, ft_m = 0.0, dtr_old = 0.0, tr_old = 0.0;
-            if (interior) {
-                ft_c = __ldg(f.ft[t] + c);
-                ft_m = k > 0 ? __ldg(f.ft[t] + c - 1) : 0.0;
-                dtr_old = a.t[t].dtracer[c];
-                tr_old = a.t[t].tr[c * 3 + taup1];
-            }
-            double xc = 0.0, xe = 0.0, xw = 0.0, xn = 0.0, xs = 0.0;
-            if (ENERGY) {
-                // int_drhodX[..., tau]: the step's contiguous copy if there is one, else the strided original
-                const bool st = a.stage_x[t] != nullptr;
-                const double* __restrict__ X = st ? a.stage_x[t] : a.t[t].int_drhodX + tau;
-                const size_t xs_ = st ? 1 : 3;
-                xc = __ldg(X + c * xs_);
-                xe = __ldg(X + (c + plane) * xs_);
-                xw = __ldg(X + (c - plane) * xs_);
-                xn = __ldg(X + (c + nz) * xs_);
-                xs = __ldg(X + (c - nz) * xs_);
-            }
-            // arithmetic + stores
-            if (interior) {
-                double e = mul(mT, add(strict::div(sub(fe_c, fe_w), b.dcdxt[q]), strict::div(sub(fn_c, fn_s), b.dcdyt[q])));
-                if (k == 0)
-                    e = add(e, strict::div(mul(mT, ft_c), lv.ddzt[0]));
-                else
-                    e = add(e, strict::div(mul(mT, sub(ft_c, ft_m)), lv.ddzt[k]));
-                a.t[t].dtracer[c] = add(dtr_old, e);        // diffusion.py:196
-                const double v = add(tr_old, mul(dt, e));  // diffusion.py:197
-                a.t[t].tr[c * 3 + taup1] = v;
-                if (!SKEW) b.R[t][s] = v;
-            }
-            if (ENERGY) {  // compute_dissipation, veros/core/diffusion.py:15-35 (on [1:-1, 1:-1])
-                const double gx = add(mul(sub(xe, xc), fe_c), mul(sub(xc, xw), fe_w));
-                const double gy = add(mul(sub(xn, xc), fn_c), mul(sub(xc, xs), fn_s));
-                f.diss[t][c] = add(strict::div(mul(fac_diss, gx), b.dcdxt[q]), strict::div(mul(fac_diss, gy), b.dcdyt[q]));
-            }
-        }
-        if (!SKEW && interior) {  // _calc_implicit_part, diffusion.py:149-164
-            const int ks = b.ksv[q];
-            const double del = (k < nz - 1) ? mul(lv.dt_dzw[k], k33) : 0.0;
-            const double delm = (k > 0) ? mul(lv.dt_dzw[k - 1], k33m) : 0.0;
-            double diag;
-            if (k == ks)
-                diag = add(1.0, strict::div(del, lv.ddzt[k]));  // b_tri_edge
-            else if (k == nz - 1)
-                diag = add(1.0, strict::div(delm, lv.ddzt[k]));
-            else
-                diag = add(1.0, strict::div(add(del, delm), lv.ddzt[k]));
-            b.D[s] = diag;
-            b.U[s] = (k < nz - 1) ? strict::div(-del, lv.ddzt[k]) : 0.0;
-            if (k > 0) b.L[s - 1] = (k > ks) ? strict::div(-delm, lv.ddzt[k]) : 0.0;
-        }
-    }
-}
-
-// phase C: one thread per water column, dgtsv on all right-hand sides
-template <int NTR>
-__device__ __forceinline__ void phase_c(const UpdConst& u, const TileBuf& b, const TileGeom& g, int tid, int nthr) {
-    if (!g.i_int) return;
-    for (int q = tid; q < g.ncols; q += nthr) {
-        const int j = g.j0 + q;
-        const int ks = b.ksv[q];
-        if (j >= 2 && j < u.M - 2 && ks >= 0) {
-            const int o = q * u.pitch;
-            dgtsv_column<NTR>(ks, u.nz, b.L + o, b.D + o, b.U + o, b.R[0] + o, b.R[NTR - 1] + o);
-        }
-    }
-}
-
-// phase D: implicit result, tendency, dissipation on the W grid
-template <int NTR, bool SKEW, bool ENERGY>
-__device__ __forceinline__ void phase_d(const DiffArgs& a, const Scratch& f, const UpdConst& u, const LevelTabs& lv,
-                                        const TileBuf& b, const TileGeom& g, int tid, int nthr) {
-    const int M = u.M, nz = u.nz, pitch = u.pitch, tau = u.tau, taup1 = u.taup1;
-    const double gr = u.gr;
-    const Divisor ddt = u.ddt;
-    // ---- phase D ----------------------------------------------------------------------------------
-    for (int idx = tid; idx < g.ncells; idx += nthr) {
-        const int q = idx / nz, k = idx - q * nz;
-        const int j = g.j0 + q;
-        const size_t c = g.base + idx;
-        const int s = q * pitch + k;
-        const bool interior = g.i_int && j >= 2 && j < M - 2;
-        const int ks = b.ksv[q];
-        const bool land = ks >= 0;
-        const bool up = k < nz - 1;
-        const bool solved = !SKEW && interior && land && k >= ks;
-        if (!ENERGY && !solved) continue;
-        // loads
-        double P = 0.0, k33 = 0.0, mW = 0.0;
-        double old[NTR], dtr_mid[NTR], d0[NTR], d1[NTR], x0[NTR], x1[NTR], ftc[NTR];
-        if (ENERGY) {
-            P = a.P_diss[c];
-            if (interior && up) {
-                k33 = __ldg(a.K_33 + c);
-                mW = (double)a.maskW[c];
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < NTR; ++t) {
-            old[t] = dtr_mid[t] = d0[t] = d1[t] = x0[t] = x1[t] = ftc[t] = 0.0;
-            if (solved) {
-                old[t] = a.t[t].tr[c * 3 + taup1];
-                dtr_mid[t] = a.t[t].dtracer[c];
-            }
-            if (ENERGY) {
-                d0[t] = f.diss[t][c];
-                if (up) d1[t] = f.diss[t][c + 1];
-                if (interior && up) {
-                    const bool st = a.stage_x[t] != nullptr;
-                    const double* __restrict__ X = st ? a.stage_x[t] : a.t[t].int_drhodX + tau;
-                    const size_t xs_ = st ? 1 : 3;
-                    x0[t] = __ldg(X + c * xs_);
-                    x1[t] = __ldg(X + (c + 1) * xs_);
-                    ftc[t] = __ldg(f.ft[t] + c);
-                }
-            }
-        }
-        // arithmetic + stores
-#pragma unroll
-        for (int t = 0; t < NTR; ++t) {
-            if (solved) {  // where(water_mask, sol, tr); diffusion.py:168,203-204
-                const double nw = b.R[t][s];
-                a.t[t].dtracer[c] = add(dtr_mid[t], strict::div(sub(nw, old[t]), ddt));
-                a.t[t].tr[c * 3 + taup1] = nw;
-            }
-            if (ENERGY) {
-                // dissipation_on_wgrid, veros/core/diffusion.py:41-62
-                double dw;
-                if (up) {
-                    const double m = mul(0.5, add(d0[t], d1[t]));
-                    const double edge = (land && k == ks) ? 1.0 : 0.0, water = (land && k > ks) ? 1.0 : 0.0;
-                    const double dzw_pad = lv.ddzw[k > 0 ? k - 1 : 0].y;
-                    dw = add(mul(add(m, mul(0.5, strict::div(mul(d0[t], dzw_pad), lv.ddzw[k]))), edge), mul(m, water));
-                } else {
-                    dw = mul(d0[t], land ? 1.0 : 0.0);
-                }
-                P = add(P, dw);  // diffusion.py:246-249
-                if (interior && up) {  // diffusion.py:254-279
-                    const double fxa = strict::div(add(-x1[t], x0[t]), lv.ddzw[k]);
-                    double v;
-                    if (SKEW) {
-                        v = mul(mul(mul(gr, fxa), ftc[t]), mW);
-                    } else {
-                        // tr[taup1] after the update: R holds it for every interior cell of the tile
-                        const double dtr = sub(b.R[t][s + 1], b.R[t][s]);
-                        v = mul(mul(gr, fxa), add(mul(ftc[t], mW), mul(strict::div(mul(k33, dtr), lv.ddzw[k]), mW)));
-                    }
-                    P = add(P, v);
-                }
-            }
-        }
-        if (ENERGY) a.P_diss[c] = P;
-    }
-}
-
-__device__ __forceinline__ UpdConst upd_const(const DiffArgs& a, int pitch, double fac_diss, double gr) {
-    UpdConst u;
-    u.N = a.g.N;
-    u.M = a.g.M;
-    u.nz = a.g.nz;
-    u.pitch = pitch;
-    u.tau = *a.tau;
-    u.taup1 = *a.taup1;
-    u.plane = (size_t)a.g.M * a.g.nz;
-    u.dt = a.dt_tracer;
-    u.fac_diss = fac_diss;
-    u.gr = gr;
-    u.ddt = make_divisor(a.dt_tracer);
-    return u;
-}
+namespace vb {
+using namespace upd;
+namespace {
 
 // ---- one tile per CTA, phases separated by CTA barriers --------------------------------------------------
 // (A persistent, warp-specialised variant -- warp 0 solving tile n while warps 1-3 stream tiles n+1 and
@@ -462,13 +196,13 @@ update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch
     fill_level_tabs(a, lv, nz, u.dt, threadIdx.x, kUpdBlock);
     fill_tile_tabs(a, u, b, g, threadIdx.x, kUpdBlock);
     __syncthreads();
-    phase_b<NTR, SKEW, ENERGY>(a, f, u, lv, b, g, threadIdx.x, kUpdBlock);
+    phase_b<NTR, SKEW, ENERGY, false>(a, f, u, lv, b, g, threadIdx.x, kUpdBlock);
     __syncthreads();  // also orders this CTA's diss[] stores before the phase D loads of its own cells
     if (!SKEW) {
         phase_c<NTR>(u, b, g, threadIdx.x, kUpdBlock);
         __syncthreads();
     }
-    phase_d<NTR, SKEW, ENERGY>(a, f, u, lv, b, g, threadIdx.x, kUpdBlock);
+    phase_d<NTR, SKEW, ENERGY, false>(a, f, u, lv, b, g, threadIdx.x, kUpdBlock);
 }
 
 template <int NTR, bool SKEW, bool ENERGY>

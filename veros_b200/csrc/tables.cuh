@@ -62,6 +62,8 @@ __device__ __forceinline__ strict::Divisor ld_div(const strict::Divisor* p) {
 }
 
 // defined in iso_pre.cu
-void launch_setup_tables(cudaStream_t s, const Grid& g, double dt_tracer, double* tables);
+// `zero` / `nzero`: unsigned ints to clear in the same launch (the fused kernel's queue and counters)
+void launch_setup_tables(cudaStream_t s, const Grid& g, double dt_tracer, double* tables, unsigned int* zero = nullptr,
+                         int nzero = 0);
 
 }  // namespace vb
