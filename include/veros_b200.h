@@ -73,10 +73,11 @@ typedef struct VerosB200SolveDescriptor {
  * top faces) instantiation instead of choosing by grid size.  Results are identical either way. */
 #define VEROS_B200_FLAG_PRE_SINGLE 8
 #define VEROS_B200_FLAG_PRE_SPLIT 16
-/* iso_step: run the step as separate launches (table setup, TEOS-10 pass, slope + flux kernel(s), update kernel)
- * instead of the one persistent kernel that is the default.  Same results bit for bit; kept for A/B measurements and
- * so that the parity tests cover the kernels the stand-alone ops use. */
-#define VEROS_B200_FLAG_STEP_CLASSIC 32
+/* iso_step: run the whole step as ONE persistent kernel (csrc/iso_mega.cu: all phases as dependency-ordered work
+ * items, inter-phase scratch in an L2-resident ring) instead of separate launches (table setup, TEOS-10 pass, slope +
+ * flux kernel(s), update kernel).  Same results bit for bit.  Opt-in: measured slower than the separate launches on
+ * every grid, kept with its parity tests and measurements. */
+#define VEROS_B200_FLAG_STEP_FUSED 32
 
 /* Static (jit-constant) facts of the isoneutral ops: shapes and the settings of
  * veros/settings.py:24-91 that the path reads. */
@@ -175,6 +176,11 @@ void veros_b200_vertmix_tempsalt_f64(void* stream, void** buffers, const char* o
 size_t veros_b200_iso_pre_workspace_bytes(const char* opaque, size_t opaque_len);
 size_t veros_b200_iso_diffusion_workspace_bytes(const char* opaque, size_t opaque_len);
 size_t veros_b200_iso_step_workspace_bytes(const char* opaque, size_t opaque_len);
+
+/* Byte offset, inside the iso_step workspace, of 16 uint64 scheduling statistics the fused step kernel leaves behind
+ * (development aid): [t] ns its CTAs spent waiting for dependencies before items of type t, [5+t] ns spent working on
+ * them, [10+t] number of items; t = 1 TEOS-10, 2 staging copy, 3 slopes+fluxes, 4 update. */
+size_t veros_b200_iso_step_stats_offset(const char* opaque, size_t opaque_len);
 
 /* Sticky error state: 0 = ok; otherwise a cudaError_t value or VEROS_B200_ERR_*. */
 #define VEROS_B200_ERR_BAD_DESCRIPTOR 100001

@@ -32,6 +32,10 @@ for name in sys.argv[1:] or ["bench_1M", "global_1deg", "global_4deg", "acc"]:
     states = [IsoState.from_numpy(st, "cuda:0") for _ in range(2 if name != "bench_1M" else 3)]
     plans = {id(s): isoneutral.StepPlan(s) for s in states}
     t_step = timeit(lambda s: plans[id(s)](), states)
+    if os.environ.get("VEROS_B200_MEGA_STATS"):
+        plans[id(states[0])]()
+        torch.cuda.synchronize()
+        print(f"{name}: scheduling stats {isoneutral.step_stats(states[0])}")
     for pl in plans.values():
         pl.capture()
     t_graph = timeit(lambda s: plans[id(s)](), states)

@@ -34,17 +34,14 @@ def dev():
 # Kernel variants every fixture is run through (VERDICT r1 "parity hole": the split launches
 # iso_pre_kernel<EOS,.,3> + <EOS,.,4> are what large grids -- i.e. the benchmark -- execute, the single launch
 # <EOS,.,7> is what small grids execute; the descriptor flags force either on any size).
-# "mega" is the default implementation of the fused step (one persistent kernel, csrc/iso_mega.cu); "single" and
-# "split" run the step as separate launches (VEROS_B200_FLAG_STEP_CLASSIC) with the named slope-kernel variant, which
-# is also what the stand-alone isoneutral_diffusion_pre op executes.
+# "mega" runs the fused step as one persistent kernel (csrc/iso_mega.cu, VEROS_B200_FLAG_STEP_FUSED, opt-in).
 VARIANTS = ("single", "split", "mega")
 
 
 def variant_flags(variant):
     from veros_b200 import _lib
 
-    return {"auto": 0, "mega": 0, "single": _lib.FLAG_PRE_SINGLE | _lib.FLAG_STEP_CLASSIC,
-            "split": _lib.FLAG_PRE_SPLIT | _lib.FLAG_STEP_CLASSIC}[variant]
+    return {"auto": 0, "mega": _lib.FLAG_STEP_FUSED, "single": _lib.FLAG_PRE_SINGLE, "split": _lib.FLAG_PRE_SPLIT}[variant]
 
 
 def gpu_state(st, dev, variant="auto"):

@@ -23,6 +23,7 @@ HELPERS = (
     "veros_b200_iso_pre_workspace_bytes",
     "veros_b200_iso_diffusion_workspace_bytes",
     "veros_b200_iso_step_workspace_bytes",
+    "veros_b200_iso_step_stats_offset",
     "veros_b200_last_error",
     "veros_b200_last_error_string",
     "veros_b200_clear_error",
@@ -68,7 +69,7 @@ HAS_B_EDGE, HAS_D_EDGE = 1, 2
 FLAG_SKEW = 1
 FLAG_NO_WEST_RING, FLAG_NO_EAST_RING = 2, 4
 FLAG_PRE_SINGLE, FLAG_PRE_SPLIT = 8, 16
-FLAG_STEP_CLASSIC = 32
+FLAG_STEP_FUSED = 32
 
 _lib = None
 
@@ -88,7 +89,7 @@ def lib():
         fn.restype = None
         fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
     for name in ("veros_b200_iso_pre_workspace_bytes", "veros_b200_iso_diffusion_workspace_bytes",
-                 "veros_b200_iso_step_workspace_bytes"):
+                 "veros_b200_iso_step_workspace_bytes", "veros_b200_iso_step_stats_offset"):
         fn = getattr(L, name)
         fn.restype = ctypes.c_size_t
         fn.argtypes = [ctypes.c_char_p, ctypes.c_size_t]

@@ -266,7 +266,8 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     p.K_11 = (double*)B[40];
     p.K_22 = (double*)B[41];
     p.K_33 = (double*)B[42];
-    const bool classic = (d->flags & VEROS_B200_FLAG_STEP_CLASSIC) != 0 || getenv("VEROS_B200_STEP_CLASSIC") != nullptr;
+    // separate launches unless the fused persistent kernel is asked for (measured slower so far: DESIGN.md)
+    const bool classic = !((d->flags & VEROS_B200_FLAG_STEP_FUSED) != 0 || getenv("VEROS_B200_STEP_FUSED") != nullptr);
     p.dt_tracer = d->dt_tracer;
     p.eos = d->eq_of_state_type;
     p.K_iso_steep = d->K_iso_steep;
@@ -316,7 +317,7 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
         a.tables = p.tables;
         a.fluxes_ready = 1;
         prof_mark(s, 0);
-        launch_setup_tables(s, p.g, d->dt_tracer, p.tables, sync, 4 * d->nx_tot + 2);
+        launch_setup_tables(s, p.g, d->dt_tracer, p.tables, sync, (int)(2 * mega_sync_doubles(d->nx_tot)));
         if (call_failed()) return;
         prof_mark(s, 1);
         launch_iso_mega(s, p, a, ring, sync);
@@ -403,6 +404,11 @@ size_t veros_b200_iso_step_workspace_bytes(const char* opaque, size_t len) {
     const size_t fused = tabs_doubles(d) + mega_sync_doubles(d->nx_tot) +
                          mega_ring_doubles(d->nx_tot, d->ny_tot, d->nz, d->eq_of_state_type, d->enable_conserve_energy != 0);
     return 8 * (classic > fused ? classic : fused);
+}
+
+size_t veros_b200_iso_step_stats_offset(const char* opaque, size_t len) {
+    const auto* d = unpack<VerosB200IsoDescriptor>(opaque, len, "iso_step_stats_offset: bad descriptor");
+    return d ? 8 * (tabs_doubles(d) + mega_stats_offset_doubles(d->nx_tot)) : 0;
 }
 
 int veros_b200_last_error(void) { return g_err.load(); }

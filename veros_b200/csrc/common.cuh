@@ -114,6 +114,7 @@ void launch_vertmix(cudaStream_t s, const VmixArgs& a);
 // the fused persistent step kernel (iso_mega.cu)
 size_t mega_ring_doubles(int N, int M, int nz, int eos, int energy);
 size_t mega_sync_doubles(int N);
+size_t mega_stats_offset_doubles(int N);
 void launch_iso_mega(cudaStream_t s, const PreArgs& p, const DiffArgs& d, double* ring, unsigned int* sync);
 void launch_solve_implicit(cudaStream_t s, int ncol, int nz, const double* a, const double* b, const double* c,
                            const double* d, const uint8_t* water, const uint8_t* edge, const double* b_edge,

@@ -178,8 +178,8 @@ namespace {
 // functions, verified bit-identical and measured 8-10 % SLOWER on both benchmark grids: with the tile
 // double buffered only half as many columns are being solved per SM, and 12 streaming warps per SM move
 // less data than the 24 of this kernel.  DESIGN.md section 3.2.)
-template <int NTR, bool SKEW, bool ENERGY>
-__global__ void __launch_bounds__(kUpdBlock, 6)
+template <int NTR, bool SKEW, bool ENERGY, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 768 / BLOCK)
 update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch, const double fac_diss,
               const double gr) {
     extern __shared__ double sm[];
@@ -193,16 +193,16 @@ update_kernel(const DiffArgs a, const Scratch f, const int cols, const int pitch
     lv.dt_dzw = reinterpret_cast<double*>(lv.ddzw + nz);
     const TileBuf b = tile_buf_at(lv.dt_dzw + nz, cols, pitch, NTR);
     const TileGeom g = tile_geom(u, i, 1 + blockIdx.x * cols, cols);
-    fill_level_tabs(a, lv, nz, u.dt, threadIdx.x, kUpdBlock);
-    fill_tile_tabs(a, u, b, g, threadIdx.x, kUpdBlock);
+    fill_level_tabs(a, lv, nz, u.dt, threadIdx.x, BLOCK);
+    fill_tile_tabs(a, u, b, g, threadIdx.x, BLOCK);
     __syncthreads();
-    phase_b<NTR, SKEW, ENERGY, false>(a, f, u, lv, b, g, threadIdx.x, kUpdBlock);
+    phase_b<NTR, SKEW, ENERGY, false>(a, f, u, lv, b, g, threadIdx.x, BLOCK);
     __syncthreads();  // also orders this CTA's diss[] stores before the phase D loads of its own cells
     if (!SKEW) {
-        phase_c<NTR>(u, b, g, threadIdx.x, kUpdBlock);
+        phase_c<NTR>(u, b, g, threadIdx.x, BLOCK);
         __syncthreads();
     }
-    phase_d<NTR, SKEW, ENERGY, false>(a, f, u, lv, b, g, threadIdx.x, kUpdBlock);
+    phase_d<NTR, SKEW, ENERGY, false>(a, f, u, lv, b, g, threadIdx.x, BLOCK);
 }
 
 template <int NTR, bool SKEW, bool ENERGY>
@@ -223,10 +223,17 @@ void launch_update(cudaStream_t s, const DiffArgs& a, const Scratch& f) {
         cols = max(1, (M - 2 + per_row - 1) / per_row);
     }
     const size_t smem = lev_bytes + 8 * ((size_t)(3 + NTR) * cols * pitch + (size_t)cols * 4 + (cols + 1) / 2 + 1) + 16;
-    auto kern = update_kernel<NTR, SKEW, ENERGY>;
-    allow_big_smem(kern, 200 * 1024);  // per device, not per process
     dim3 grid((M - 2 + cols - 1) / cols, N - 2);
-    kern<<<grid, kUpdBlock, smem, s>>>(a, f, cols, pitch, fac_diss, gr);
+    static const int block = getenv("VEROS_B200_UPD_BLOCK") ? atoi(getenv("VEROS_B200_UPD_BLOCK")) : 128;  // tuning knob
+    if (block == 256) {
+        auto kern = update_kernel<NTR, SKEW, ENERGY, 256>;
+        allow_big_smem(kern, 200 * 1024);
+        kern<<<grid, 256, smem, s>>>(a, f, cols, pitch, fac_diss, gr);
+    } else {
+        auto kern = update_kernel<NTR, SKEW, ENERGY, 128>;
+        allow_big_smem(kern, 200 * 1024);
+        kern<<<grid, 128, smem, s>>>(a, f, cols, pitch, fac_diss, gr);
+    }
     count_launch();
     check_launch("update_kernel");
 }

@@ -13,7 +13,8 @@
 //     C(i)  contiguous copy of int_drhodT/S[i,...,tau]  (enable_conserve_energy only)
 //     P(i)  slopes, mixing tensor and fluxes of plane i (needs E(i), E(i+1))
 //     U(i)  divergence, column solve, tendencies, dissipation of plane i (needs P(i-1), P(i), C(i-1..i+1))
-// items, queued round by round as E(r), C(r), P(r-1), U(r-2).  One resident wave of CTAs pulls items from an atomic
+// items, queued round by round as E(r), C(r), P(r-lag), U(r-2 lag), the lag chosen so that dependent items are a
+// full wave of CTAs apart in the queue (a blocked item idles its SM slot).  One resident wave of CTAs pulls items from an atomic
 // counter; an item waits (thread 0 polls a per-plane completion counter) until the items it depends on have finished.
 // Dependencies only point to EARLIER queue positions and an item is owned by a CTA that is already running, so the
 // scheme cannot deadlock and needs no co-residency guarantee (no cooperative launch, capturable in a CUDA graph).
@@ -53,7 +54,9 @@ struct MegaArgs {
     int ring;       // x-planes in the scratch ring
     int cols, pitch;            // update tile: columns, shared-memory pitch
     int nE, nC, nP, nU;         // items per plane
+    int lagP, lagU;             // queue order: round r holds E(r), C(r), P(r - lagP), U(r - lagU)
     unsigned int* sync;         // [0] queue head, [1] unused, then eosDone[N], copyDone[N], preDone[N], updDone[N]
+    unsigned long long* stats;  // [type]: ns spent waiting, [5 + type]: ns spent working, [10 + type]: items (thread 0's clock)
     double fac_diss, gr;
 };
 
@@ -110,7 +113,7 @@ iso_mega_kernel(const MegaArgs m) {
     unsigned* const preDone = copyDone + N;
     unsigned* const updDone = preDone + N;
     const int per_round = m.nE + m.nC + m.nP + m.nU;
-    const int total = per_round * (N + 2);
+    const int total = per_round * (N + m.lagU);
 
     // update-side constants and per-level tables (once per CTA)
     const UpdConst u = upd_const(m.d, m.pitch, m.fac_diss, m.gr);
@@ -139,11 +142,11 @@ iso_mega_kernel(const MegaArgs m) {
         }
         w -= m.nC;
         if (w < m.nP) {
-            if (r >= 1 && r - 1 < N) { it.type = kPre; it.plane = r - 1; it.idx = w; }
+            if (r >= m.lagP && r - m.lagP < N) { it.type = kPre; it.plane = r - m.lagP; it.idx = w; }
             return it;
         }
         w -= m.nP;
-        if (r >= 3 && r - 2 <= N - 2) { it.type = kUpd; it.plane = r - 2; it.idx = w; }
+        if (r - m.lagU >= 1 && r - m.lagU <= N - 2) { it.type = kUpd; it.plane = r - m.lagU; it.idx = w; }
         return it;
     };
 
@@ -183,9 +186,16 @@ iso_mega_kernel(const MegaArgs m) {
         }
     };
 
+    unsigned long long t_start = 0;  // thread 0: when the current item's work began
     if (threadIdx.x == 0) {
         const int g = (int)atomicAdd(queue, 1u);
-        if (g < total) wait_deps(decode(g));
+        const unsigned long long t0 = global_ns();
+        if (g < total) {
+            const Item nx = decode(g);
+            wait_deps(nx);
+            t_start = global_ns();
+            atomicAdd(m.stats + nx.type, t_start - t0);
+        }
         s_next = g;
     }
     __syncthreads();
@@ -261,8 +271,17 @@ iso_mega_kernel(const MegaArgs m) {
         if (threadIdx.x == 0) {
             unsigned* done = it.type == kEos ? eosDone : it.type == kCopy ? copyDone : it.type == kPre ? preDone : updDone;
             if (it.type != kNone) add_release(done + i);
+            const unsigned long long t0 = global_ns();
+            atomicAdd(m.stats + 5 + it.type, t0 - t_start);
+            atomicAdd(m.stats + 10 + it.type, 1ull);
             const int gn = (int)atomicAdd(queue, 1u);
-            if (gn < total) wait_deps(decode(gn));
+            t_start = t0;
+            if (gn < total) {
+                const Item nx = decode(gn);
+                wait_deps(nx);
+                t_start = global_ns();
+                atomicAdd(m.stats + nx.type, t_start - t0);
+            }
             s_next = gn;
         }
         __syncthreads();
@@ -274,7 +293,7 @@ iso_mega_kernel(const MegaArgs m) {
 namespace {
 
 struct MegaPlan {
-    int ring, cols, pitch, nE, nC, nP, nU;
+    int ring, cols, pitch, nE, nC, nP, nU, lagP, lagU;
     size_t smem;
 };
 
@@ -301,11 +320,18 @@ MegaPlan mega_plan(int N, int M, int nz, int eos, int energy) {
     q.nC = energy ? (plane_cells + kMegaCopyCells - 1) / kMegaCopyCells : 0;
     q.nP = (plane_cells + kMegaPreCells - 1) / kMegaPreCells;
     q.nU = (M - 2 + cols - 1) / cols;
-    // ring: enough planes that a full wave of CTAs (<= 4 per SM on <= 160 SMs) never waits for a slot to be recycled
+    // Queue order.  A CTA that pulls an item whose producers are still running blocks (and idles its SM slot), so
+    // dependent items are queued `lag` rounds apart, where one lag covers more items than there are resident CTAs
+    // (<= 4 per SM on <= 160 SMs): by the time U(i) is pulled, every P(i) item was pulled a full wave earlier.
     const int per_round = q.nE + q.nC + q.nP + q.nU;
-    int ring = 8 + (2 * 640 + per_round - 1) / per_round;
-    if (const char* e = getenv("VEROS_B200_MEGA_RING")) ring = std::max(4, atoi(e));  // tuning knob
-    q.ring = std::min(ring, N);
+    int lag = 1 + (640 + per_round - 1) / per_round;
+    if (const char* e = getenv("VEROS_B200_MEGA_LAG")) lag = std::max(1, atoi(e));  // tuning knob
+    lag = std::min(lag, N);
+    q.lagP = lag;
+    q.lagU = 2 * lag;
+    // ring: planes in flight between the first producer and the last consumer, plus slack so that recycling a slot
+    // never waits either
+    q.ring = std::min(2 * lag + lag + 4, N);
     return q;
 }
 
@@ -317,7 +343,8 @@ size_t mega_ring_doubles(int N, int M, int nz, int eos, int energy) {
     const MegaPlan q = mega_plan(N, M, nz, eos, energy);
     return (size_t)12 * q.ring * M * nz;
 }
-size_t mega_sync_doubles(int N) { return ((size_t)4 * N + 2 + 1) / 2 + 1; }
+size_t mega_sync_doubles(int N) { return ((size_t)4 * N + 2 + 1) / 2 + 1 + 16; }  // + 16 statistics words
+size_t mega_stats_offset_doubles(int N) { return ((size_t)4 * N + 2 + 1) / 2 + 1; }
 
 // ring + sync memory start at `scratch`; tables have been built (and `sync` zeroed) by launch_setup_tables
 void launch_iso_mega(cudaStream_t s, const PreArgs& p0, const DiffArgs& d0, double* scratch, unsigned int* sync) {
@@ -334,6 +361,9 @@ void launch_iso_mega(cudaStream_t s, const PreArgs& p0, const DiffArgs& d0, doub
     m.nP = q.nP;
     m.nU = q.nU;
     m.sync = sync;
+    m.stats = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(sync) + mega_stats_offset_doubles(N));
+    m.lagP = q.lagP;
+    m.lagU = q.lagU;
     m.fac_diss = 0.5 * d0.grav / d0.rho_0;  // diffusion.py (core) :19-21, Python float arithmetic
     m.gr = -d0.grav / d0.rho_0;             // isoneutral/diffusion.py:259,268
     const size_t rp = (size_t)q.ring * M * nz;
@@ -364,7 +394,7 @@ void launch_iso_mega(cudaStream_t s, const PreArgs& p0, const DiffArgs& d0, doub
     m.p.m2c0 = -2.0 * m.p.iso_slopec / m.p.iso_dslope;
     m.p.s_max = (345.0 + m.p.iso_slopec / m.p.iso_dslope) * m.p.iso_dslope;
 
-    const int total = (q.nE + q.nC + q.nP + q.nU) * (N + 2);
+    const int total = (q.nE + q.nC + q.nP + q.nU) * (N + q.lagU);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

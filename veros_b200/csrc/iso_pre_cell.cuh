@@ -172,6 +172,10 @@ __device__ __forceinline__ void pre_cell(const PreArgs& a, const Tables& tb, con
         const double Kcm = __ldg(a.K_iso + c + km);
         const double rdzt4 = L1.d4zt.ry;
 
+        // The triad (density point (i,j,k), east face of the cell, level k below the top face) enters both the east
+        // face (ip = 0, kr = 1) and the top face (ip = 1, kr = 0) with bit-identical slope and taper; likewise in y.
+        // When one launch computes all faces the top face reuses them: 14 tapers per cell instead of 16.
+        double sh_sx = 0.0, sh_tsx = 0.0, sh_sy = 0.0, sh_tsy = 0.0;
         // ---- east face: Ai_ez, K_11 (isoneutral.py:100-132) and flux_east (diffusion.py:25-47) ------
         double Te = 0.0, Se = 0.0, Tpe = 0.0, Spe = 0.0;  // (i+1,j,k), (i+1,j,k+1)
         if (inE || inT) {
@@ -217,6 +221,7 @@ __device__ __forceinline__ void pre_cell(const PreArgs& a, const Tables& tb, con
                     const double tp = taper(sxe);
                     sumz = fma(wz[kr], fmax(a.K_iso_steep, diffloc * tp), sumz);
                     A[ip][kr] = tp * sxe;  // maskU is already in gTxc/gSxc
+                    if (kr == 1 && ip == 0) { sh_sx = sxe; sh_tsx = A[ip][kr]; }
                 }
             }
             double* out = a.Ai_ez + c * 4;
@@ -282,6 +287,7 @@ __device__ __forceinline__ void pre_cell(const PreArgs& a, const Tables& tb, con
                     const double tp = taper(syn);
                     sumz = fma(wz[kr], fmax(a.K_iso_steep, diffloc * tp), sumz);
                     A[jp][kr] = tp * syn;
+                    if (kr == 1 && jp == 0) { sh_sy = syn; sh_tsy = A[jp][kr]; }
                 }
             }
             double* out = a.Ai_nz + c * 4;
@@ -347,19 +353,29 @@ __device__ __forceinline__ void pre_cell(const PreArgs& a, const Tables& tb, con
                 const double nrden = -rcp_fast(neg_part_minus_eps(drodzb));
 #pragma unroll
                 for (int ip = 0; ip < 2; ++ip) {
-                    const double drodxb = fma(dS_, dSx[ip][kr] * mx[ip][kr], dT_ * (dTx[ip][kr] * mx[ip][kr]));
-                    const double sxb = drodxb * nrden;
-                    const double tp = taper(sxb);
-                    const double ts = tp * sxb;
+                    double sxb, ts;
+                    if (doE && kr == 0 && ip == 1) {  // = the east face's (ip = 0, kr = 1) triad
+                        sxb = sh_sx;
+                        ts = sh_tsx;
+                    } else {
+                        const double drodxb = fma(dS_, dSx[ip][kr] * mx[ip][kr], dT_ * (dTx[ip][kr] * mx[ip][kr]));
+                        sxb = drodxb * nrden;
+                        ts = taper(sxb) * sxb;
+                    }
                     sumx = fma(cx[ip], ts * sxb, sumx);
                     Ax[ip][kr] = sel(mWc1, ts);
                 }
 #pragma unroll
                 for (int jp = 0; jp < 2; ++jp) {
-                    const double drodyb = fma(dS_, dSy[jp][kr] * my[jp][kr], dT_ * (dTy[jp][kr] * my[jp][kr]));
-                    const double syb = drodyb * nrden;
-                    const double tp = taper(syb);
-                    const double ts = tp * syb;
+                    double syb, ts;
+                    if (doN && kr == 0 && jp == 1) {  // = the north face's (jp = 0, kr = 1) triad
+                        syb = sh_sy;
+                        ts = sh_tsy;
+                    } else {
+                        const double drodyb = fma(dS_, dSy[jp][kr] * my[jp][kr], dT_ * (dTy[jp][kr] * my[jp][kr]));
+                        syb = drodyb * nrden;
+                        ts = taper(syb) * syb;
+                    }
                     sumy = fma(cy[jp], ts * syb, sumy);
                     Ay[jp][kr] = sel(mWc1, ts);
                 }

@@ -90,6 +90,17 @@ def step_workspace_bytes(state):
     return int(_lib.lib().veros_b200_iso_step_workspace_bytes(opaque, len(opaque)))
 
 
+def step_stats(state):
+    """Scheduling statistics of the last fused step on `state` (development aid): per item type the time its CTAs
+    spent waiting for dependencies / working (summed over CTAs, microseconds) and the number of items."""
+    opaque = bytes(_descriptor(state))
+    off = int(_lib.lib().veros_b200_iso_step_stats_offset(opaque, len(opaque)))
+    ws = state.workspace(_lib.lib().veros_b200_iso_step_workspace_bytes(opaque, len(opaque)))
+    raw = ws.view(torch.int64)[off // 8: off // 8 + 16].cpu().tolist()
+    names = {1: "eos", 2: "copy", 3: "pre", 4: "update"}
+    return {n: dict(wait_us=raw[t] / 1e3, work_us=raw[5 + t] / 1e3, items=raw[10 + t]) for t, n in names.items()}
+
+
 class StepPlan:
     """`isoneutral_step(state)` with the argument marshalling done once.
 
