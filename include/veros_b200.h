@@ -73,6 +73,14 @@ typedef struct VerosB200SolveDescriptor {
  * top faces) instantiation instead of choosing by grid size.  Results are identical either way. */
 #define VEROS_B200_FLAG_PRE_SINGLE 8
 #define VEROS_B200_FLAG_PRE_SPLIT 16
+/* Masked cells.  By default the kernels do not compute what the masks force to zero: a face whose maskU / maskV /
+ * maskW is 0 only stores the zeros the reference's expressions produce there (exact for finite fields, any masks),
+ * and the fused step leaves dry cells (maskT = 0) of the tracers, tendencies and P_diss_iso alone, which equals the
+ * reference bit for bit when the masks are the ones Veros derives from kbot (veros/core/numerics.py:200-221: maskT from
+ * kbot, maskU/V/W the staggered minima).  Warps that lie entirely below the sea floor or on land then cost nothing.
+ * This flag turns the shortcut off (every cell is computed; for inputs with inconsistent masks or non-finite values
+ * on land). */
+#define VEROS_B200_FLAG_NO_MASK_SKIP 64
 /* iso_step: run the whole step as ONE persistent kernel (csrc/iso_mega.cu: all phases as dependency-ordered work
  * items, inter-phase scratch in an L2-resident ring) instead of separate launches (table setup, TEOS-10 pass, slope +
  * flux kernel(s), update kernel).  Same results bit for bit.  Opt-in: measured slower than the separate launches on

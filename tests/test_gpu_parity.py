@@ -35,13 +35,15 @@ def dev():
 # iso_pre_kernel<EOS,.,3> + <EOS,.,4> are what large grids -- i.e. the benchmark -- execute, the single launch
 # <EOS,.,7> is what small grids execute; the descriptor flags force either on any size).
 # "mega" runs the fused step as one persistent kernel (csrc/iso_mega.cu, VEROS_B200_FLAG_STEP_FUSED, opt-in).
-VARIANTS = ("single", "split", "mega")
+# "noskip" computes masked faces and dry cells too (VEROS_B200_FLAG_NO_MASK_SKIP) instead of storing their zeros.
+VARIANTS = ("single", "split", "mega", "noskip")
 
 
 def variant_flags(variant):
     from veros_b200 import _lib
 
-    return {"auto": 0, "mega": _lib.FLAG_STEP_FUSED, "single": _lib.FLAG_PRE_SINGLE, "split": _lib.FLAG_PRE_SPLIT}[variant]
+    return {"auto": 0, "mega": _lib.FLAG_STEP_FUSED, "single": _lib.FLAG_PRE_SINGLE, "split": _lib.FLAG_PRE_SPLIT,
+            "noskip": _lib.FLAG_NO_MASK_SKIP}[variant]
 
 
 def gpu_state(st, dev, variant="auto"):

@@ -70,6 +70,7 @@ FLAG_SKEW = 1
 FLAG_NO_WEST_RING, FLAG_NO_EAST_RING = 2, 4
 FLAG_PRE_SINGLE, FLAG_PRE_SPLIT = 8, 16
 FLAG_STEP_FUSED = 32
+FLAG_NO_MASK_SKIP = 64
 
 _lib = None
 

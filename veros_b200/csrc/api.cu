@@ -178,6 +178,7 @@ void veros_b200_iso_pre_f64(void* stream, void** B, const char* opaque, size_t l
     a.drdS = a.drdT + n3;
     a.with_flux = 0;
     a.with_stage = 0;
+    a.no_mask_skip = (d->flags & VEROS_B200_FLAG_NO_MASK_SKIP) ? 1 : 0;
     a.variant = pre_variant(d);
     a.stage[0] = a.stage[1] = nullptr;
     a.stage_src[0] = a.stage_src[1] = nullptr;
@@ -226,6 +227,7 @@ void veros_b200_iso_diffusion_f64(void* stream, void** B, const char* opaque, si
     a.skip_west_ring = (d->flags & VEROS_B200_FLAG_NO_WEST_RING) ? 1 : 0;
     a.skip_east_ring = (d->flags & VEROS_B200_FLAG_NO_EAST_RING) ? 1 : 0;
     a.fluxes_ready = 0;
+    a.dry_skip = 0;  // stand-alone op: fluxes come from caller-supplied Ai_* / K_*, nothing is assumed about them
     a.stage_x[0] = a.stage_x[1] = nullptr;
     a.dt_tracer = d->dt_tracer;
     a.grav = d->grav;
@@ -276,6 +278,7 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     p.stage_src[0] = (const double*)B[29];
     p.stage_src[1] = (const double*)B[30];
     p.variant = pre_variant(d);
+    p.no_mask_skip = (d->flags & VEROS_B200_FLAG_NO_MASK_SKIP) ? 1 : 0;
 
     DiffArgs a;
     a.g = p.g;
@@ -307,6 +310,7 @@ void veros_b200_iso_step_f64(void* stream, void** B, const char* opaque, size_t 
     a.dt_tracer = d->dt_tracer;
     a.grav = d->grav;
     a.rho_0 = d->rho_0;
+    a.dry_skip = p.no_mask_skip ? 0 : 1;
 
     if (!classic) {
         // ---- the fused persistent kernel (iso_mega.cu): tables | queue + counters | scratch ring --------------------

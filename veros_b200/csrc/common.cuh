@@ -64,6 +64,7 @@ struct PreArgs {
     const double* stage_src[2];
     double* stage[2];
     int with_stage;
+    int no_mask_skip;  // compute masked faces too instead of storing their zeros (VEROS_B200_FLAG_NO_MASK_SKIP)
     int variant;  // 0: by size, 1: one launch for all faces, 2: east+north / top launches (VEROS_B200_FLAG_PRE_*)
     int eos;
     double K_iso_steep, iso_slopec, iso_dslope;
@@ -88,6 +89,7 @@ struct DiffArgs {
     int skew, energy;
     int skip_west_ring, skip_east_ring;  // sub-slab mode (VEROS_B200_FLAG_NO_*_RING)
     int fluxes_ready;  // the fused slope+flux kernel already filled the flux workspace
+    int dry_skip;      // fused step: cells with maskT = 0 are left alone (see iso_update_phases.cuh)
     const double* stage_x[2];   // contiguous copies of int_drhodX[..., tau] made by the slope kernel (or null)
     double* tables;    // metric tables (tables.cuh), built by launch_setup_tables
     double dt_tracer, grav, rho_0;

@@ -111,7 +111,36 @@ __device__ __forceinline__ void pre_cell(const PreArgs& a, const Tables& tb, con
     const bool inT = doT && (i >= 2 && i < N - 2 && j >= 2 && j < M - 2 && k < nz - 1);
     double fl[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};  // [tracer][east, north, top]
 
-    if (inE || inN || inT) {
+    // Masked faces.  Where maskU (east face), maskV (north face) or maskW (top face) of the cell is 0 the reference's
+    // expressions reduce to exact zeros for finite fields: the masked gradient makes every slope of the face 0, so
+    // Ai = taper * 0 = 0, the diffusivity sums carry the mask as a factor, and the fluxes multiply zeros
+    // (isoneutral.py:64-95,115-131,196-222).  Such faces only STORE those zeros; a warp whose 32 cells need nothing
+    // else skips all loads and arithmetic -- below the sea floor and on land that is every warp (about half of the
+    // cells of a global grid with realistic bathymetry).
+    const bool skip = !a.no_mask_skip;
+    const bool needE = inE && !(skip && a.maskU[c] == 0);
+    const bool needN = inN && !(skip && a.maskV[c] == 0);
+    const bool needT = inT && !(skip && a.maskW[c] == 0);
+    auto zero_face = [&](double* Ai, double* Kxx, bool all_kr) {
+        double* out = Ai + c * 4;
+        if (all_kr) {
+            store_pair(out, 0.0, 0.0);
+            store_pair(out + 2, 0.0, 0.0);
+        } else {  // k = 0 of an east / north face: the kr = 0 entries are never written
+            out[1] = 0.0;
+            out[3] = 0.0;
+        }
+        Kxx[c] = 0.0;
+    };
+    if (inE && !needE) zero_face(a.Ai_ez, a.K_11, k >= 1);
+    if (inN && !needN) zero_face(a.Ai_nz, a.K_22, k >= 1);
+    if (inT && !needT) {
+        zero_face(a.Ai_bx, a.K_33, true);
+        store_pair(a.Ai_by + c * 4, 0.0, 0.0);
+        store_pair(a.Ai_by + c * 4 + 2, 0.0, 0.0);
+    }
+
+    if (needE || needN || needT) {
         auto ld = [](const double* f, size_t cell) { return __ldg(f + cell * 3); };
         const bool hasKm = k >= 1, hasKp = k < nz - 1;
         const int km = hasKm ? -1 : 0, kp = hasKp ? 1 : 0;  // clamped neighbours (pad_z_edges)
@@ -121,8 +150,8 @@ __device__ __forceinline__ void pre_cell(const PreArgs& a, const Tables& tb, con
         // next to their use behind the stores to the same array, where nothing could hide the miss.
         double Aez_old[2] = {0.0, 0.0}, Anz_old[2] = {0.0, 0.0};
         if (FLUX && !hasKm) {
-            if (inE) { Aez_old[0] = a.Ai_ez[c * 4]; Aez_old[1] = a.Ai_ez[c * 4 + 2]; }
-            if (inN) { Anz_old[0] = a.Ai_nz[c * 4]; Anz_old[1] = a.Ai_nz[c * 4 + 2]; }
+            if (needE) { Aez_old[0] = a.Ai_ez[c * 4]; Aez_old[1] = a.Ai_ez[c * 4 + 2]; }
+            if (needN) { Anz_old[0] = a.Ai_nz[c * 4]; Anz_old[1] = a.Ai_nz[c * 4 + 2]; }
         }
         // metric table entries of this level / row / plane (read-only path, L1 resident)
         struct { Divisor d4zt; double rdzw, dzw, pabs; } L1, L0;
@@ -178,7 +207,7 @@ __device__ __forceinline__ void pre_cell(const PreArgs& a, const Tables& tb, con
         double sh_sx = 0.0, sh_tsx = 0.0, sh_sy = 0.0, sh_tsy = 0.0;
         // ---- east face: Ai_ez, K_11 (isoneutral.py:100-132) and flux_east (diffusion.py:25-47) ------
         double Te = 0.0, Se = 0.0, Tpe = 0.0, Spe = 0.0;  // (i+1,j,k), (i+1,j,k+1)
-        if (inE || inT) {
+        if (needE || needT) {
             Te = ld(T, ce);
             Se = ld(S, ce);
             Tpe = ld(T, ce + kp);
@@ -187,7 +216,7 @@ __device__ __forceinline__ void pre_cell(const PreArgs& a, const Tables& tb, con
         const double dTxc = Te - Tc, dSxc = Se - Sc;  // raw east differences at level k
         const double mrdx = sel(a.maskU[c] != 0, Rj.cdxu.ry);
         const double gTxc = dTxc * mrdx, gSxc = dSxc * mrdx;  // dTdx(i,j,k)
-        if (inE) {
+        if (needE) {
             const double Tme = ld(T, ce + km), Sme = ld(S, ce + km);
             const double dT0e = Te - Tme, dS0e = Se - Sme, dT1e = Tpe - Te, dS1e = Spe - Se;
             const bool mWe1 = hasKp && a.maskW[ce], mWe0 = hasKm && a.maskW[ce + km];
@@ -244,7 +273,7 @@ __device__ __forceinline__ void pre_cell(const PreArgs& a, const Tables& tb, con
 
         // ---- north face: Ai_nz, K_22 (isoneutral.py:137-168) and flux_north (diffusion.py:52-77) ----
         double Tn = 0.0, Sn = 0.0, Tpn = 0.0, Spn = 0.0;  // (i,j+1,k), (i,j+1,k+1)
-        if (inN || inT) {
+        if (needN || needT) {
             Tn = ld(T, cn);
             Sn = ld(S, cn);
             Tpn = ld(T, cn + kp);
@@ -253,7 +282,7 @@ __device__ __forceinline__ void pre_cell(const PreArgs& a, const Tables& tb, con
         const double dTyc = Tn - Tc, dSyc = Sn - Sc;
         const double mrdy = sel(a.maskV[c] != 0, Rj.dyu.ry);
         const double gTyc = dTyc * mrdy, gSyc = dSyc * mrdy;  // dTdy(i,j,k)
-        if (inN) {
+        if (needN) {
             const double Tmn = ld(T, cn + km), Smn = ld(S, cn + km);
             const double dT0n = Tn - Tmn, dS0n = Sn - Smn, dT1n = Tpn - Tn, dS1n = Spn - Sn;
             const bool mWn1 = hasKp && a.maskW[cn], mWn0 = hasKm && a.maskW[cn + km];
@@ -310,7 +339,7 @@ __device__ __forceinline__ void pre_cell(const PreArgs& a, const Tables& tb, con
         }
 
         // ---- top face: Ai_bx, Ai_by, K_33 (isoneutral.py:173-225) and flux_top (diffusion.py:85-111) --
-        if (inT) {
+        if (needT) {
             struct { Divisor dyu; double cosu, facty; } Rs;
             {
                 const RowTab* r = tb.row + j - 1;

@@ -123,6 +123,17 @@ __device__ __forceinline__ void phase_b(const DiffArgs& a, const Scratch& f, con
         if (!interior && !ENERGY) continue;
         const size_t c = g.base + idx;
         const int s = q * pitch + k;
+        // Dry cells (fused step, masks consistent with kbot as veros/core/numerics.py:200-221 builds them): the explicit
+        // tendency is maskT * (...) = 0, so tracer and tendency keep their values bit for bit; every flux around the
+        // cell is masked, so its dissipation is 0; the column solve starts above it.  Nothing to load, nothing to
+        // store but that zero (phase D of the wet cell above may read it).
+        if (a.dry_skip && a.maskT[c] == 0) {
+            if (ENERGY) {
+#pragma unroll
+                for (int t = 0; t < NTR; ++t) f.diss[t][g.db + idx] = 0.0;
+            }
+            continue;
+        }
         const double mT = interior ? (double)a.maskT[c] : 0.0;
         double k33 = 0.0, k33m = 0.0;
         if (!SKEW && interior) {
@@ -230,6 +241,7 @@ __device__ __forceinline__ void phase_d(const DiffArgs& a, const Scratch& f, con
         const bool up = k < nz - 1;
         const bool solved = !SKEW && interior && land && k >= ks;
         if (!ENERGY && !solved) continue;
+        if (a.dry_skip && a.maskT[c] == 0) continue;  // dissipation_on_wgrid and the vertical term are exact zeros there
         // loads
         double P = 0.0, k33 = 0.0, mW = 0.0;
         double old[NTR], dtr_mid[NTR], d0[NTR], d1[NTR], x0[NTR], x1[NTR], ftc[NTR];
