@@ -113,6 +113,24 @@ typedef struct VerosB200VmixDescriptor {
     double dt_tracer;
 } VerosB200VmixDescriptor;
 
+/* implicit_vert_friction and isoneutral_diag_streamfunction: sizes (and the momentum time step). */
+typedef struct VerosB200ColumnDescriptor {
+    int32_t nx_tot; /* N = nx + 4 */
+    int32_t ny_tot; /* M = ny + 4 */
+    int32_t nz;
+    int32_t flags; /* reserved, 0 */
+    double dt;     /* dt_mom for implicit_vert_friction; unused otherwise */
+} VerosB200ColumnDescriptor;
+
+/* set_eke_diffusivities: sizes and the settings of veros/settings.py that veros/core/eke.py:34-85 reads. */
+typedef struct VerosB200EkeDescriptor {
+    int32_t nx_tot, ny_tot, nz;
+    int32_t enable_eke;
+    int32_t enable_eke_isopycnal_diffusion;
+    int32_t flags; /* reserved, 0 */
+    double pi, eke_lmin, eke_cross, eke_crhin, eke_k_max, eke_c_k, K_gm_0, K_iso_0;
+} VerosB200EkeDescriptor;
+
 /* ------------------------------------------------------------------------------ compute ops */
 
 /* Column solve on the model's native (X,Y,nz) z-contiguous layout, replacing
@@ -178,6 +196,28 @@ void veros_b200_iso_step_f64(void* stream, void** buffers, const char* opaque, s
  * (results): 9 temp, 10 salt, 11 dtemp_vmix, 12 dsalt_vmix (N,M,nz; every element written) */
 void veros_b200_vertmix_tempsalt_f64(void* stream, void** buffers, const char* opaque, size_t opaque_len);
 
+/* SURVEY.md 8f rank 3 -- the first other caller of solve_implicit with its coefficient assembly fused in:
+ * implicit_vert_friction, veros/core/friction.py:92-205 (both velocity components, du_mix / dv_mix, the dissipation
+ * through ugrid_to_tgrid / vgrid_to_tgrid, numerics.py:313-336, added to K_diss_v).  Bit-identical to the NumPy backend.
+ * opaque: VerosB200ColumnDescriptor (dt = dt_mom).
+ * buffers (operands): 0 u, 1 v (N,M,nz,3), 2 du_mix, 3 dv_mix, 4 K_diss_v (N,M,nz), 5 tau, 6 taup1 (int32[1]),
+ *          7 kappaM (N,M,nz), 8 maskU, 9 maskV (u8), 10 kbot (int32 N,M), 11 dzt, 12 dzw (nz), 13 dxt, 14 dxu (N),
+ *          15 area_v, 16 area_t (N,M)
+ * (results): 17..21 = operands 0..4, 22 workspace (2 * N*M*nz doubles) */
+void veros_b200_implicit_vert_friction_f64(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
+/* SURVEY.md 8f rank 4, consumer of the path's outputs: isoneutral_diag_streamfunction_kernel,
+ * veros/core/isoneutral/isoneutral.py:232-258.  opaque: VerosB200ColumnDescriptor.
+ * buffers (operands): 0 K_gm, 1 Ai_ez, 2 Ai_nz, 3 B1_gm, 4 B2_gm | (results): 5 B1_gm, 6 B2_gm */
+void veros_b200_iso_diag_streamfunction_f64(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
+/* SURVEY.md 8f rank 4, producer of K_gm / K_iso: set_eke_diffusivities_kernel, veros/core/eke.py:34-85 (NumPy's
+ * pairwise order of the Rossby-radius column sum included).  opaque: VerosB200EkeDescriptor.
+ * buffers (operands): 0 Nsqr, 1 eke (N,M,nz,3), 2 tau (int32[1]), 3 maskW (u8), 4 dzw (nz), 5 coriolis_t, 6 beta (N,M)
+ * (results): 7 L_rossby (N,M), 8 L_rhines, 9 eke_len, 10 sqrteke, 11 K_gm, 12 K_iso (N,M,nz)
+ * With enable_eke == 0 only K_gm and K_iso are written and buffers 0..10 are not touched. */
+void veros_b200_set_eke_diffusivities_f64(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
 /* ------------------------------------------------------------------------ host-side helpers */
 
 /* Scratch the caller must provide as the last result (0 is possible; then pass any valid pointer). */
@@ -232,7 +272,7 @@ void veros_b200_ipc_close(void* base);
 void veros_b200_profile_events(void** events, int n);
 
 int veros_b200_abi_version(void);
-/* sizeof() of descriptor 0 = Tridiag, 1 = Solve, 2 = Iso, 3 = Vmix as compiled into the library. */
+/* sizeof() of descriptor 0 = Tridiag, 1 = Solve, 2 = Iso, 3 = Vmix, 4 = Column, 5 = Eke as compiled into the library. */
 size_t veros_b200_descriptor_size(int which);
 /* Number of kernel launches enqueued by this library since load (bench.py's gpu_launches). */
 unsigned long long veros_b200_launch_count(void);

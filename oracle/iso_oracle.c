@@ -653,3 +653,198 @@ void oracle_vertmix_tempsalt(int32_t N, int32_t M, int32_t nz, int32_t taup1, in
                         trs[t][TIDX(g, j, k, taup1)] = trs[t][TIDX(N - 4 + g, j, k, taup1)];
                     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * implicit_vert_friction (veros/core/friction.py:92-205): implicit vertical friction of u and v with
+ * kappaM (two solve_implicit calls with b_edge), the du_mix / dv_mix tendencies and the dissipation
+ * added to K_diss_v after ugrid_to_tgrid / vgrid_to_tgrid (veros/core/numerics.py:313-336).
+ * the first extra solve_implicit caller.  Golden vectors
+ * tests/golden/fric_*.npz (bit-for-bit).
+ * u, v: (N,M,nz,3); kappaM, du_mix, dv_mix, K_diss_v: (N,M,nz); maskU, maskV: u8 (N,M,nz);
+ * kbot: (N,M); dxt, dxu: (N); area_v, area_t: (N,M).
+ * ---------------------------------------------------------------------------------------- */
+void oracle_implicit_vert_friction(int32_t N, int32_t M, int32_t nz, int32_t tau, int32_t taup1, double dt_mom,
+                                   double *u, double *v, const double *kappaM, const uint8_t *maskU,
+                                   const uint8_t *maskV, const int32_t *kbot, const double *dzt, const double *dzw,
+                                   const double *dxt, const double *dxu, const double *area_v, const double *area_t,
+                                   double *du_mix, double *dv_mix, double *K_diss_v, int32_t tdma_mode) {
+    const size_t n3 = (size_t)N * M * nz;
+    double *vel[2] = {u, v};
+    double *dmix[2] = {du_mix, dv_mix};
+    const uint8_t *mask[2] = {maskU, maskV};
+    for (int comp = 0; comp < 2; comp++) {
+        double *diss = calloc(n3, 8); /* :100, zeros outside [1:-2, 1:-2, :-1] */
+        double *w = vel[comp];
+        const uint8_t *m = mask[comp];
+#pragma omp parallel
+        {
+        double *a = calloc(nz, 8), *b = calloc(nz, 8), *c = calloc(nz, 8), *d = calloc(nz, 8), *delta = calloc(nz, 8);
+        double *be = calloc(nz, 8), *fxa = calloc(nz, 8), *x = calloc(nz, 8), *w1 = calloc(nz, 8), *w2 = calloc(nz, 8);
+        uint8_t *water = calloc(nz, 1), *edge = calloc(nz, 1);
+#pragma omp for schedule(static)
+        for (int i = 1; i < N - 2; i++)
+            for (int j = 1; j < M - 2; j++) {
+                const int in = comp == 0 ? i + 1 : i, jn = comp == 0 ? j : j + 1; /* the cell on the other side of the face */
+                const int kb0 = kbot[i * M + j], kb1 = kbot[in * M + jn];
+                const int ks = (kb0 > kb1 ? kb0 : kb1) - 1; /* :111 / :158, create_water_masks */
+                const int land = ks >= 0;
+                for (int k = 0; k < nz; k++) {
+                    water[k] = land && k >= ks;
+                    edge[k] = land && k == ks;
+                    if (k < nz - 1) {
+                        fxa[k] = 0.5 * (kappaM[IDX(i, j, k)] + kappaM[IDX(in, jn, k)]);                           /* :114 */
+                        delta[k] = dt_mom / dzw[k] * fxa[k] * (double)m[IDX(i, j, k + 1)] * (double)m[IDX(i, j, k)]; /* :115-117 */
+                    } else {
+                        fxa[k] = 0.0;
+                        delta[k] = 0.0;
+                    }
+                }
+                for (int k = 0; k < nz; k++) {
+                    a[k] = (k >= 1) ? -delta[k - 1] / dzt[k] : 0.0;      /* :118 */
+                    b[k] = (k >= 1) ? 1 + delta[k - 1] / dzt[k] : 0.0;   /* :119 */
+                    if (k >= 1 && k < nz - 1) b[k] = b[k] + delta[k] / dzt[k]; /* :120 */
+                    be[k] = 1 + delta[k] / dzt[k];                       /* :121 */
+                    c[k] = -delta[k] / dzt[k];                           /* :122 (u) / :173-174 (v: last level +0) */
+                    d[k] = w[TIDX(i, j, k, tau)];                        /* :123 */
+                    if (edge[k]) b[k] = be[k];
+                }
+                if (comp == 1) c[nz - 1] = 0.0;
+                solve_column(nz, a, b, c, d, water, edge, x, w1, w2, tdma_mode); /* :125 */
+                for (int k = 0; k < nz; k++) {
+                    if (water[k]) w[TIDX(i, j, k, taup1)] = x[k];                                     /* :126 */
+                    dmix[comp][IDX(i, j, k)] = (w[TIDX(i, j, k, taup1)] - w[TIDX(i, j, k, tau)]) / dt_mom; /* :127-129 */
+                }
+                for (int k = 0; k < nz - 1; k++) { /* :134-148 */
+                    const double ft = fxa[k] * (w[TIDX(i, j, k + 1, taup1)] - w[TIDX(i, j, k, taup1)]) / dzw[k] *
+                                      (double)m[IDX(i, j, k + 1)] * (double)m[IDX(i, j, k)];
+                    diss[IDX(i, j, k)] = (w[TIDX(i, j, k + 1, tau)] - w[TIDX(i, j, k, tau)]) * ft / dzw[k];
+                }
+            }
+        free(a); free(b); free(c); free(d); free(delta); free(be); free(fxa); free(x); free(w1); free(w2);
+        free(water); free(edge);
+        }
+        /* ugrid_to_tgrid / vgrid_to_tgrid on the whole array, then K_diss_v += (:150-151, :202-203) */
+        for (int i = 0; i < N; i++)
+            for (int j = 0; j < M; j++)
+                for (int k = 0; k < nz; k++) {
+                    double t = diss[IDX(i, j, k)];
+                    if (comp == 0 && i >= 2 && i < N - 2)
+                        t = (dxu[i] * diss[IDX(i, j, k)] + dxu[i - 1] * diss[IDX(i - 1, j, k)]) / (2 * dxt[i]);
+                    if (comp == 1 && j >= 2 && j < M - 2)
+                        t = (area_v[i * M + j] * diss[IDX(i, j, k)] + area_v[i * M + j - 1] * diss[IDX(i, j - 1, k)]) /
+                            (2 * area_t[i * M + j]);
+                    K_diss_v[IDX(i, j, k)] = K_diss_v[IDX(i, j, k)] + t;
+                }
+        free(diss);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * isoneutral_diag_streamfunction_kernel (veros/core/isoneutral/isoneutral.py:232-258): B1_gm, B2_gm from
+ * K_gm and the Ai_ez / Ai_nz the path just produced (consumer).
+ * np.sum(..., axis=(3, 4)) of a C-contiguous (...,2,2) block adds its four elements in memory order.
+ * ---------------------------------------------------------------------------------------- */
+void oracle_diag_streamfunction(int32_t N, int32_t M, int32_t nz, const double *K_gm, const double *Ai_ez,
+                                const double *Ai_nz, double *B1_gm, double *B2_gm) {
+    for (int i = 1; i < N - 2; i++)
+        for (int j = 1; j < M - 2; j++)
+            for (int k = 0; k < nz; k++) {
+                const int km = k > 0 ? k - 1 : 0; /* pad_z_edges */
+                if (j >= 2) { /* :241-245, [1:-2, 2:-2] */
+                    const double diffloc = 0.25 * (K_gm[IDX(i, j, k)] + K_gm[IDX(i, j, km)] + K_gm[IDX(i + 1, j, k)] +
+                                                   K_gm[IDX(i + 1, j, km)]);
+                    const double *A = Ai_ez + IDX(i, j, k) * 4;
+                    const double s = ((A[0] + A[1]) + A[2]) + A[3];
+                    B2_gm[IDX(i, j, k)] = 0.25 * diffloc * s;
+                }
+                if (i >= 2) { /* :250-254, [2:-2, 1:-2] */
+                    const double diffloc = 0.25 * (K_gm[IDX(i, j, k)] + K_gm[IDX(i, j, km)] + K_gm[IDX(i, j + 1, k)] +
+                                                   K_gm[IDX(i, j + 1, km)]);
+                    const double *A = Ai_nz + IDX(i, j, k) * 4;
+                    const double s = ((A[0] + A[1]) + A[2]) + A[3];
+                    B1_gm[IDX(i, j, k)] = -0.25 * diffloc * s;
+                }
+            }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * set_eke_diffusivities_kernel (veros/core/eke.py:34-85): the producer of K_gm and K_iso
+ * (SURVEY.md 8(f) rank 4).  The column sum of :44-51 is NumPy's add.reduce over a contiguous axis: the
+ * accumulator starts from the identity 0 and the run goes through pairwise summation (8 interleaved
+ * accumulators up to 128 elements, recursive halving above; numpy/_core/src/umath/loops_utils.h.src,
+ * numpy 2.3 as installed) -- sum_variant 1, pinned by tests/golden/eke_*.npz (variant 0, first element
+ * outside the pairwise run, does NOT reproduce the reference).
+ * ---------------------------------------------------------------------------------------- */
+static double np_pairwise_sum(const double *a, int64_t n) {
+    if (n < 8) {
+        double res = 0.;
+        for (int64_t i = 0; i < n; i++) res += a[i];
+        return res;
+    } else if (n <= 128) {
+        double r[8];
+        int64_t i;
+        for (i = 0; i < 8; i++) r[i] = a[i];
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int q = 0; q < 8; q++) r[q] += a[i + q];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    } else {
+        int64_t n2 = n / 2;
+        n2 -= n2 % 8;
+        return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+    }
+}
+
+double oracle_np_sum(const double *a, int64_t n, int32_t variant) {
+    if (n == 0) return 0.0;
+    if (variant == 0) return a[0] + np_pairwise_sum(a + 1, n - 1);
+    return 0.0 + np_pairwise_sum(a, n);
+}
+
+void oracle_set_eke_diffusivities(int32_t N, int32_t M, int32_t nz, int32_t tau, int32_t enable_eke,
+                                  int32_t enable_eke_isopycnal_diffusion, double pi, double eke_lmin, double eke_cross,
+                                  double eke_crhin, double eke_k_max, double eke_c_k, double K_gm_0, double K_iso_0,
+                                  const double *Nsqr, const double *eke, const uint8_t *maskW, const double *dzw,
+                                  const double *coriolis_t, const double *beta, double *L_rossby, double *L_rhines,
+                                  double *eke_len, double *sqrteke, double *K_gm, double *K_iso, int32_t sum_variant) {
+    const size_t n3 = (size_t)N * M * nz;
+    if (!enable_eke) { /* :73-82 */
+        for (size_t c = 0; c < n3; c++) {
+            K_gm[c] = K_gm_0;
+            K_iso[c] = K_iso_0;
+        }
+        return;
+    }
+    double *term = malloc(8 * (size_t)nz);
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < M; j++) {
+            for (int k = 0; k < nz; k++) { /* :44-50 */
+                const double n2 = Nsqr[TIDX(i, j, k, tau)];
+                term[k] = sqrt(n2 > 0.0 ? n2 : 0.0) * dzw[k] * (double)maskW[IDX(i, j, k)] / pi;
+            }
+            const double C = oracle_np_sum(term, nz, sum_variant);
+            const double f = fabs(coriolis_t[i * M + j]);
+            const double b2 = 2 * beta[i * M + j];
+            const double l1 = C / (f > 1e-16 ? f : 1e-16);
+            const double l2 = sqrt(C / (b2 > 1e-16 ? b2 : 1e-16));
+            const double Lr = l1 < l2 ? l1 : l2; /* :52-54 */
+            L_rossby[i * M + j] = Lr;
+            const double bt = beta[i * M + j] > 1e-16 ? beta[i * M + j] : 1e-16;
+            for (int k = 0; k < nz; k++) {
+                const double e = eke[TIDX(i, j, k, tau)];
+                const double se = sqrt(e > 0.0 ? e : 0.0); /* :59 */
+                const double lrh = sqrt(se / bt);           /* :60 */
+                const double x1 = eke_cross * Lr, x2 = eke_crhin * lrh;
+                const double mn = x1 < x2 ? x1 : x2;
+                const double len = eke_lmin > mn ? eke_lmin : mn; /* :61-64 */
+                const double kg = eke_c_k * len * se;
+                sqrteke[IDX(i, j, k)] = se;
+                L_rhines[IDX(i, j, k)] = lrh;
+                eke_len[IDX(i, j, k)] = len;
+                K_gm[IDX(i, j, k)] = eke_k_max < kg ? eke_k_max : kg; /* :65 */
+                K_iso[IDX(i, j, k)] = enable_eke_isopycnal_diffusion ? K_gm[IDX(i, j, k)] : K_iso_0; /* :75-78 */
+            }
+        }
+    free(term);
+}

@@ -168,3 +168,49 @@ def solve_implicit(a, b, c, d, water_mask, edge_mask, b_edge=None, d_edge=None, 
 
 def solve_tridiagonal(a, b, c, d, water_mask, edge_mask, mode=0):
     return solve_implicit(a, b, c, d, water_mask, edge_mask, mode=mode)
+
+
+def implicit_vert_friction(st, tdma_mode=0):
+    """veros/core/friction.py:92-205 in place on st["u"|"v"] (time level taup1), st["du_mix"|"dv_mix"|"K_diss_v"]."""
+    N, M, nz = st["kappaM"].shape
+    for k in ("u", "v", "du_mix", "dv_mix", "K_diss_v"):
+        st[k] = _f64(st[k]).copy()
+    args = [st["u"], st["v"], _f64(st["kappaM"]), _u8(st["maskU"]), _u8(st["maskV"]),
+            np.ascontiguousarray(st["kbot"], dtype=np.int32)]
+    args += [_f64(st[k]) for k in ("dzt", "dzw", "dxt", "dxu", "area_v", "area_t")]
+    args += [st["du_mix"], st["dv_mix"], st["K_diss_v"]]
+    lib().oracle_implicit_vert_friction(
+        ctypes.c_int32(N), ctypes.c_int32(M), ctypes.c_int32(nz), ctypes.c_int32(int(st["tau"])),
+        ctypes.c_int32(int(st["taup1"])), ctypes.c_double(float(st["dt_mom"])), *[_p(a) for a in args],
+        ctypes.c_int32(tdma_mode))
+    return st
+
+
+def isoneutral_diag_streamfunction(st):
+    """veros/core/isoneutral/isoneutral.py:232-258 in place on st["B1_gm"|"B2_gm"]."""
+    N, M, nz = st["K_gm"].shape
+    st["B1_gm"], st["B2_gm"] = _f64(st["B1_gm"]).copy(), _f64(st["B2_gm"]).copy()
+    lib().oracle_diag_streamfunction(ctypes.c_int32(N), ctypes.c_int32(M), ctypes.c_int32(nz), _p(_f64(st["K_gm"])),
+                                     _p(_f64(st["Ai_ez"])), _p(_f64(st["Ai_nz"])), _p(st["B1_gm"]), _p(st["B2_gm"]))
+    return st
+
+
+def set_eke_diffusivities(st, sum_variant=1):
+    """veros/core/eke.py:34-85; returns the dict of arrays the reference's KernelOutput carries."""
+    N, M, nz = st["K_gm"].shape
+    on = bool(st["enable_eke"])
+    out = {k: np.zeros((N, M, nz)) for k in ("L_rhines", "eke_len", "sqrteke", "K_gm", "K_iso")}
+    out["L_rossby"] = np.zeros((N, M))
+    dummy3, dummy2 = np.zeros((N, M, nz, 3)), np.zeros((N, M))
+    g = lambda k, d: _f64(st[k]) if (on and k in st) else d
+    lib().oracle_set_eke_diffusivities(
+        ctypes.c_int32(N), ctypes.c_int32(M), ctypes.c_int32(nz), ctypes.c_int32(int(st.get("tau", 0))),
+        ctypes.c_int32(int(on)), ctypes.c_int32(int(bool(st["enable_eke_isopycnal_diffusion"]))),
+        *[ctypes.c_double(float(st[k])) for k in ("pi", "eke_lmin", "eke_cross", "eke_crhin", "eke_k_max", "eke_c_k", "K_gm_0", "K_iso_0")],
+        _p(g("Nsqr", dummy3)), _p(g("eke", dummy3)), _p(_u8(st["maskW"]) if "maskW" in st else np.zeros((N, M, nz), np.uint8)),
+        _p(g("dzw", np.zeros(nz))), _p(g("coriolis_t", dummy2)), _p(g("beta", dummy2)),
+        _p(out["L_rossby"]), _p(out["L_rhines"]), _p(out["eke_len"]), _p(out["sqrteke"]), _p(out["K_gm"]), _p(out["K_iso"]),
+        ctypes.c_int32(sum_variant))
+    if not on:
+        return {"K_gm": out["K_gm"], "K_iso": out["K_iso"]}
+    return out

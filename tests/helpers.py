@@ -12,7 +12,7 @@ KS = ("K_11", "K_22", "K_33")
 
 def golden_names():
     names = (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return sorted(n for n in names if not n.startswith("vmix_"))
+    return sorted(n for n in names if not n.startswith(("vmix_", "fric_", "sf_", "eke_")))
 
 
 def load_golden(name):
@@ -35,6 +35,16 @@ def load_golden(name):
 
 def vmix_golden_names():
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("vmix_") and f.endswith(".npz"))
+
+
+def io_golden_names(prefix):
+    """Fixtures of the neighbouring kernels (make_golden_next.py): fric_*, sf_*, eke_*."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith(prefix) and f.endswith(".npz"))
+
+
+def load_io_golden(name):
+    """(inputs and settings keyed by reference names, outputs) of an in__/set__/out__ fixture."""
+    return load_vmix_golden(name)
 
 
 def load_vmix_golden(name):

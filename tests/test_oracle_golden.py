@@ -146,3 +146,33 @@ def test_oracle_vertmix_tempsalt_bitexact(name):
     got = oracle.vertmix_tempsalt(helpers.copy_state(st))
     for k in ("temp", "salt", "dtemp_vmix", "dsalt_vmix"):
         assert np.array_equal(got[k], out[k]), k
+
+
+# ------------------------------------------------------------------ neighbours of the path
+@pytest.mark.parametrize("name", helpers.io_golden_names("fric_"))
+def test_oracle_implicit_vert_friction_bitexact(name):
+    """veros/core/friction.py:92-205 (two solve_implicit calls with b_edge, tendencies, dissipation through
+    ugrid_to_tgrid / vgrid_to_tgrid): bit for bit against the reference's NumPy backend."""
+    st, out = helpers.load_io_golden(name)
+    got = oracle.implicit_vert_friction(helpers.copy_state(st))
+    for k in ("u", "v", "du_mix", "dv_mix", "K_diss_v"):
+        assert np.array_equal(got[k], out[k]), k
+
+
+@pytest.mark.parametrize("name", helpers.io_golden_names("sf_"))
+def test_oracle_diag_streamfunction_bitexact(name):
+    st, out = helpers.load_io_golden(name)
+    got = oracle.isoneutral_diag_streamfunction(helpers.copy_state(st))
+    for k in ("B1_gm", "B2_gm"):
+        assert np.array_equal(got[k], out[k]), k
+
+
+@pytest.mark.parametrize("name", helpers.io_golden_names("eke_"))
+def test_oracle_set_eke_diffusivities_bitexact(name):
+    """veros/core/eke.py:34-85 incl. NumPy's pairwise order of the column sum (nz = 9: 8-accumulator block + tail,
+    nz = 140: recursive halving) and the enable_eke = False branch."""
+    st, out = helpers.load_io_golden(name)
+    got = oracle.set_eke_diffusivities(helpers.copy_state(st))
+    assert set(got) == set(out)
+    for k in out:
+        assert np.array_equal(got[k], out[k]), k

@@ -18,6 +18,9 @@ OPS = (
     "veros_b200_iso_diffusion_f64",
     "veros_b200_iso_step_f64",
     "veros_b200_vertmix_tempsalt_f64",
+    "veros_b200_implicit_vert_friction_f64",
+    "veros_b200_iso_diag_streamfunction_f64",
+    "veros_b200_set_eke_diffusivities_f64",
 )
 HELPERS = (
     "veros_b200_iso_pre_workspace_bytes",
@@ -63,6 +66,19 @@ class IsoDescriptor(ctypes.Structure):
 class VmixDescriptor(ctypes.Structure):
     _fields_ = [("nx_tot", ctypes.c_int32), ("ny_tot", ctypes.c_int32), ("nz", ctypes.c_int32),
                 ("flags", ctypes.c_int32), ("dt_tracer", ctypes.c_double)]
+
+
+class ColumnDescriptor(ctypes.Structure):
+    _fields_ = [("nx_tot", ctypes.c_int32), ("ny_tot", ctypes.c_int32), ("nz", ctypes.c_int32),
+                ("flags", ctypes.c_int32), ("dt", ctypes.c_double)]
+
+
+class EkeDescriptor(ctypes.Structure):
+    _fields_ = [("nx_tot", ctypes.c_int32), ("ny_tot", ctypes.c_int32), ("nz", ctypes.c_int32),
+                ("enable_eke", ctypes.c_int32), ("enable_eke_isopycnal_diffusion", ctypes.c_int32),
+                ("flags", ctypes.c_int32)] + \
+               [(k, ctypes.c_double) for k in ("pi", "eke_lmin", "eke_cross", "eke_crhin", "eke_k_max", "eke_c_k",
+                                               "K_gm_0", "K_iso_0")]
 
 
 HAS_B_EDGE, HAS_D_EDGE = 1, 2
@@ -119,7 +135,8 @@ def lib():
     L.veros_b200_profile_events.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
     if L.veros_b200_abi_version() != ABI_VERSION:
         raise RuntimeError("libveros_b200.so ABI version mismatch; rebuild with `python -m veros_b200.build --force`")
-    for which, cls in enumerate((TridiagDescriptor, SolveDescriptor, IsoDescriptor, VmixDescriptor)):
+    for which, cls in enumerate((TridiagDescriptor, SolveDescriptor, IsoDescriptor, VmixDescriptor, ColumnDescriptor,
+                                 EkeDescriptor)):
         if L.veros_b200_descriptor_size(which) != ctypes.sizeof(cls):
             raise RuntimeError(f"descriptor layout mismatch for {cls.__name__}")
     _lib = L

@@ -22,6 +22,7 @@ SOURCES = {
     "iso_pre.cu": [],
     "iso_diffusion.cu": [],
     "iso_mega.cu": [],
+    "next_ops.cu": [],
     "halo.cu": [],
     "vertmix.cu": [],
 }

@@ -385,6 +385,42 @@ void veros_b200_vertmix_tempsalt_f64(void* stream, void** B, const char* opaque,
     launch_vertmix(s, a);
 }
 
+void veros_b200_implicit_vert_friction_f64(void* stream, void** B, const char* opaque, size_t len) {
+    begin_call();
+    const auto* d = unpack<VerosB200ColumnDescriptor>(opaque, len, "implicit_vert_friction: bad descriptor");
+    if (!d) return;
+    if (d->nx_tot < 4 || d->ny_tot < 4 || d->nz < 1 || !(d->dt > 0.0))
+        return set_error(VEROS_B200_ERR_BAD_ARGUMENT, "implicit_vert_friction: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n3 = (size_t)d->nx_tot * d->ny_tot * d->nz;
+    alias_copy(s, B[17], B[0], n3 * 24);
+    alias_copy(s, B[18], B[1], n3 * 24);
+    for (int q = 2; q < 5; ++q) alias_copy(s, B[17 + q], B[q], n3 * 8);
+    launch_implicit_vert_friction(s, d->nx_tot, d->ny_tot, d->nz, d->dt, B);
+}
+
+void veros_b200_iso_diag_streamfunction_f64(void* stream, void** B, const char* opaque, size_t len) {
+    begin_call();
+    const auto* d = unpack<VerosB200ColumnDescriptor>(opaque, len, "iso_diag_streamfunction: bad descriptor");
+    if (!d) return;
+    if (d->nx_tot < 4 || d->ny_tot < 4 || d->nz < 1)
+        return set_error(VEROS_B200_ERR_BAD_ARGUMENT, "iso_diag_streamfunction: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n3 = (size_t)d->nx_tot * d->ny_tot * d->nz;
+    alias_copy(s, B[5], B[3], n3 * 8);
+    alias_copy(s, B[6], B[4], n3 * 8);
+    launch_diag_streamfunction(s, d->nx_tot, d->ny_tot, d->nz, B);
+}
+
+void veros_b200_set_eke_diffusivities_f64(void* stream, void** B, const char* opaque, size_t len) {
+    begin_call();
+    const auto* d = unpack<VerosB200EkeDescriptor>(opaque, len, "set_eke_diffusivities: bad descriptor");
+    if (!d) return;
+    if (d->nx_tot < 1 || d->ny_tot < 1 || d->nz < 1)
+        return set_error(VEROS_B200_ERR_BAD_ARGUMENT, "set_eke_diffusivities: bad argument");
+    launch_set_eke_diffusivities((cudaStream_t)stream, d, B);
+}
+
 void veros_b200_profile_events(void** events, int n) {
     g_prof_events = reinterpret_cast<cudaEvent_t*>(events);
     g_prof_n = events ? n : 0;
@@ -434,6 +470,8 @@ extern "C" size_t veros_b200_descriptor_size(int which) {
     case 1: return sizeof(VerosB200SolveDescriptor);
     case 2: return sizeof(VerosB200IsoDescriptor);
     case 3: return sizeof(VerosB200VmixDescriptor);
+    case 4: return sizeof(VerosB200ColumnDescriptor);
+    case 5: return sizeof(VerosB200EkeDescriptor);
     default: return 0;
     }
 }

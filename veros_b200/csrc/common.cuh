@@ -113,6 +113,10 @@ void prof_mark(cudaStream_t s, int q);  // api.cu: records the q-th profiling ev
 size_t diffusion_workspace_doubles(int N, int M, int nz, int ntr);
 void launch_iso_diffusion_ws(cudaStream_t s, const DiffArgs& a, double* workspace);
 void launch_vertmix(cudaStream_t s, const VmixArgs& a);
+// neighbours of the path (next_ops.cu); B = the custom call's buffer list
+void launch_implicit_vert_friction(cudaStream_t s, int N, int M, int nz, double dt_mom, void** B);
+void launch_diag_streamfunction(cudaStream_t s, int N, int M, int nz, void** B);
+void launch_set_eke_diffusivities(cudaStream_t s, const VerosB200EkeDescriptor* d, void** B);
 // the fused persistent step kernel (iso_mega.cu)
 size_t mega_ring_doubles(int N, int M, int nz, int eos, int energy);
 size_t mega_sync_doubles(int N);

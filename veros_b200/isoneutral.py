@@ -84,6 +84,19 @@ def isoneutral_skew_diffusion(state, tr, istemp):
     _diffusion(state, tr, istemp, skew=True)
 
 
+def isoneutral_diag_streamfunction(state):
+    """Horizontal components of the eddy-driven streamfunction from K_gm and the Ai_ez / Ai_nz the path produced
+    (veros/core/isoneutral/isoneutral.py:232-269); returns KernelOutput(B1_gm, B2_gm) like the reference kernel."""
+    vs, st = state.variables, state.settings
+    for name in ("K_gm", "Ai_ez", "Ai_nz", "B1_gm", "B2_gm"):
+        if getattr(vs, name, None) is None:
+            raise ValueError(f"isoneutral_diag_streamfunction needs variable {name}")
+    desc = _lib.ColumnDescriptor(nx_tot=st.nx + 4, ny_tot=st.ny + 4, nz=st.nz, flags=0, dt=0.0)
+    operands = [vs.K_gm, vs.Ai_ez, vs.Ai_nz, vs.B1_gm, vs.B2_gm]
+    _lib.call("veros_b200_iso_diag_streamfunction_f64", _ptrs(operands + [vs.B1_gm, vs.B2_gm]), desc, _stream(state))
+    return KernelOutput(B1_gm=vs.B1_gm, B2_gm=vs.B2_gm)
+
+
 def step_workspace_bytes(state):
     """Scratch the fused step needs for `state` (veros_b200_iso_step_workspace_bytes)."""
     opaque = bytes(_descriptor(state))
