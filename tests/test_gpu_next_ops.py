@@ -48,10 +48,13 @@ def friction_state(nx, ny, nz, seed, kappa_sign=False):
     islands, masks from kbot; kappaM positive (model-like) or of random sign (interchanges in dgtsv)."""
     from veros_b200 import synthetic
 
-    base = synthetic.random_state(nx, ny, nz, seed=seed)
+    base = synthetic.random_state(nx, ny, max(nz, 2), seed=seed)
     rng = np.random.default_rng(seed + 100)
     N, M = nx + 4, ny + 4
-    st = {k: base[k] for k in ("kbot", "maskU", "maskV", "dzt", "dzw", "dxt", "dxu", "tau", "taup1")}
+    st = {k: base[k] for k in ("dxt", "dxu", "tau", "taup1")}
+    st["kbot"] = np.minimum(base["kbot"], nz).astype(np.int32)
+    _, st["maskU"], st["maskV"], _ = synthetic.masks_from_kbot(st["kbot"], nz, False)
+    st["dzt"], st["dzw"] = base["dzt"][:nz].copy(), base["dzw"][:nz].copy()
     st["u"], st["v"] = rng.standard_normal((2, N, M, nz, 3))
     kap = rng.standard_normal((N, M, nz))
     st["kappaM"] = kap if kappa_sign else np.abs(kap) * 1e-2
