@@ -131,6 +131,16 @@ typedef struct VerosB200EkeDescriptor {
     double pi, eke_lmin, eke_cross, eke_crhin, eke_k_max, eke_c_k, K_gm_0, K_iso_0;
 } VerosB200EkeDescriptor;
 
+/* advect_tempsalt: sizes and the settings veros/core/thermodynamics.py:10-62,223-245 reads. */
+#define VEROS_B200_ADVECT_SUPERBEE 1 /* settings.enable_superbee_advection */
+#define VEROS_B200_ADVECT_NO_AB 2    /* tendencies only (advect_temperature / advect_salinity), no Adams-Bashforth step */
+typedef struct VerosB200AdvectDescriptor {
+    int32_t nx_tot, ny_tot, nz;
+    int32_t flags; /* VEROS_B200_ADVECT_* */
+    double dt_tracer;
+    double AB_eps;
+} VerosB200AdvectDescriptor;
+
 /* ------------------------------------------------------------------------------ compute ops */
 
 /* Column solve on the model's native (X,Y,nz) z-contiguous layout, replacing
@@ -218,6 +228,16 @@ void veros_b200_iso_diag_streamfunction_f64(void* stream, void** buffers, const 
  * With enable_eke == 0 only K_gm and K_iso are written and buffers 0..10 are not touched. */
 void veros_b200_set_eke_diffusivities_f64(void* stream, void** buffers, const char* opaque, size_t opaque_len);
 
+/* SURVEY.md 8f rank 4, producer of temp/salt[..., taup1]: advect_temperature + advect_salinity
+ * (veros/core/thermodynamics.py:43-62 -> advect_tracer :10-40 with adv_flux_2nd / adv_flux_superbee,
+ * veros/core/advection.py:8-115) and the Adams-Bashforth step (:223-245), one pass for both tracers.
+ * opaque: VerosB200AdvectDescriptor.
+ * buffers (operands): 0 temp, 1 salt, 2 dtemp, 3 dsalt (N,M,nz,3), 4 tau, 5 taup1, 6 taum1 (int32[1]),
+ *          7 u, 8 v, 9 w (N,M,nz,3), 10 maskT, 11 maskU, 12 maskV, 13 maskW (u8), 14 dxt (N), 15 dyt (M), 16 dzt (nz),
+ *          17 cost, 18 cosu (M)
+ * (results): 19 temp, 20 salt, 21 dtemp, 22 dsalt = operands 0..3 */
+void veros_b200_advect_tempsalt_f64(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
 /* ------------------------------------------------------------------------ host-side helpers */
 
 /* Scratch the caller must provide as the last result (0 is possible; then pass any valid pointer). */
@@ -272,7 +292,7 @@ void veros_b200_ipc_close(void* base);
 void veros_b200_profile_events(void** events, int n);
 
 int veros_b200_abi_version(void);
-/* sizeof() of descriptor 0 = Tridiag, 1 = Solve, 2 = Iso, 3 = Vmix, 4 = Column, 5 = Eke as compiled into the library. */
+/* sizeof() of descriptor 0 = Tridiag, 1 = Solve, 2 = Iso, 3 = Vmix, 4 = Column, 5 = Eke, 6 = Advect as compiled into the library. */
 size_t veros_b200_descriptor_size(int which);
 /* Number of kernel launches enqueued by this library since load (bench.py's gpu_launches). */
 unsigned long long veros_b200_launch_count(void);

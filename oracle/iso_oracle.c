@@ -848,3 +848,95 @@ void oracle_set_eke_diffusivities(int32_t N, int32_t M, int32_t nz, int32_t tau,
         }
     free(term);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * advect_tracer (veros/core/thermodynamics.py:10-40) with adv_flux_2nd / adv_flux_superbee
+ * (veros/core/advection.py:8-115), advect_temperature / advect_salinity (:43-62) and the Adams-Bashforth
+ * step of :223-245 -- the producer of temp/salt[..., taup1] right before the isoneutral path
+ * (SURVEY.md 8(f) rank 4).  Golden vectors tests/golden/adv_*.npz (bit-for-bit).
+ * ---------------------------------------------------------------------------------------- */
+static double clipd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+/* one superbee face flux: values at sm1, s, sp1, sp2 and masks at sm1, s, sp1 (advection.py:39-49) */
+static double superbee_face(double vm1, double v0, double v1, double v2, double mm1, double m0, double m1, double vel,
+                            double velc, double dt, double dx) {
+    const double eps = 1e-20;
+    const double rjp = (v2 - v1) * m1, rj = (v1 - v0) * m0, rjm = (v0 - vm1) * mm1;
+    const double num = vel > 0.0 ? rjm : rjp;
+    const double den = fabs(rj) < eps ? eps : rj;
+    const double c = num / den;
+    const double a1 = clipd(2 * c, 0, 1), a2 = clipd(c, 0, 2);
+    const double cr = a1 > a2 ? a1 : a2;
+    const double uCFL = fabs(velc * dt / dx);
+    return velc * (v1 + v0) * 0.5 - fabs(velc) * ((1.0 - cr) + uCFL * cr) * rj * 0.5;
+}
+
+/* tr: (N,M,nz,3) at time level `lev`; u, v, w at time level tau; dtr: (N,M,nz) fully written */
+void oracle_advect_tracer(int32_t N, int32_t M, int32_t nz, int32_t superbee, int32_t tau, int32_t lev, double dt_tracer,
+                          const double *tr, const double *u, const double *v, const double *w, const uint8_t *maskT,
+                          const uint8_t *maskU, const uint8_t *maskV, const uint8_t *maskW, const double *dxt,
+                          const double *dyt, const double *dzt, const double *cost, const double *cosu, double *dtr) {
+    const size_t n3 = (size_t)N * M * nz;
+    double *fe = calloc(n3, 8), *fn = calloc(n3, 8), *ft = calloc(n3, 8);
+#define VAR(i, j, k) tr[TIDX(i, j, k, lev)]
+#define KC(k) ((k) < 0 ? 0 : ((k) > nz - 1 ? nz - 1 : (k)))
+#pragma omp parallel for schedule(static)
+    for (int i = 1; i < N - 2; i++)
+        for (int j = 1; j < M - 2; j++)
+            for (int k = 0; k < nz; k++) {
+                if (j >= 2) { /* east face, [1:-2, 2:-2, :] */
+                    const double vel = u[TIDX(i, j, k, tau)];
+                    if (superbee)
+                        fe[IDX(i, j, k)] = superbee_face(VAR(i - 1, j, k), VAR(i, j, k), VAR(i + 1, j, k), VAR(i + 2, j, k),
+                                                         maskU[IDX(i - 1, j, k)], maskU[IDX(i, j, k)], maskU[IDX(i + 1, j, k)],
+                                                         vel, vel, dt_tracer, cost[j] * dxt[i]);
+                    else
+                        fe[IDX(i, j, k)] = 0.5 * (VAR(i, j, k) + VAR(i + 1, j, k)) * vel * maskU[IDX(i, j, k)];
+                }
+                if (i >= 2) { /* north face, [2:-2, 1:-2, :] */
+                    const double vel = v[TIDX(i, j, k, tau)];
+                    if (superbee)
+                        fn[IDX(i, j, k)] = superbee_face(VAR(i, j - 1, k), VAR(i, j, k), VAR(i, j + 1, k), VAR(i, j + 2, k),
+                                                         maskV[IDX(i, j - 1, k)], maskV[IDX(i, j, k)], maskV[IDX(i, j + 1, k)],
+                                                         vel, vel * cosu[j], dt_tracer, cost[j] * dyt[j]);
+                    else
+                        fn[IDX(i, j, k)] = cosu[j] * 0.5 * (VAR(i, j, k) + VAR(i, j + 1, k)) * vel * maskV[IDX(i, j, k)];
+                }
+                if (i >= 2 && j >= 2 && k < nz - 1) { /* top face, [2:-2, 2:-2, :-1]; pad_z_edges clamps */
+                    const double vel = w[TIDX(i, j, k, tau)];
+                    if (superbee)
+                        ft[IDX(i, j, k)] = superbee_face(VAR(i, j, KC(k - 1)), VAR(i, j, k), VAR(i, j, k + 1), VAR(i, j, KC(k + 2)),
+                                                         maskW[IDX(i, j, KC(k - 1))], maskW[IDX(i, j, k)], maskW[IDX(i, j, k + 1)],
+                                                         vel, vel, dt_tracer, dzt[k]);
+                    else
+                        ft[IDX(i, j, k)] = 0.5 * (VAR(i, j, k) + VAR(i, j, k + 1)) * vel * maskW[IDX(i, j, k)];
+                }
+            }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < M; j++)
+            for (int k = 0; k < nz; k++) {
+                double d = 0.0;
+                if (i >= 2 && i < N - 2 && j >= 2 && j < M - 2) /* thermodynamics.py:24-35 */
+                    d = maskT[IDX(i, j, k)] * (-(fe[IDX(i, j, k)] - fe[IDX(i - 1, j, k)]) / (cost[j] * dxt[i]) -
+                                               (fn[IDX(i, j, k)] - fn[IDX(i, j - 1, k)]) / (cost[j] * dyt[j]));
+                const double mt = -1 * (int)maskT[IDX(i, j, k)];
+                if (k == 0)
+                    d = d + mt * ft[IDX(i, j, 0)] / dzt[0]; /* :36 */
+                else
+                    d = d + mt * (ft[IDX(i, j, k)] - ft[IDX(i, j, k - 1)]) / dzt[k]; /* :37-39 */
+                dtr[IDX(i, j, k)] = d;
+            }
+#undef VAR
+#undef KC
+    free(fe); free(fn); free(ft);
+}
+
+/* Adams-Bashforth step (thermodynamics.py:223-245) of one tracer over the whole array */
+void oracle_adams_bashforth(int32_t N, int32_t M, int32_t nz, int32_t tau, int32_t taup1, int32_t taum1, double dt_tracer,
+                            double AB_eps, double *tr, const double *dtr, const uint8_t *maskT) {
+    const size_t n3 = (size_t)N * M * nz;
+    for (size_t c = 0; c < n3; c++)
+        tr[c * 3 + taup1] = tr[c * 3 + tau] +
+                            dt_tracer * ((1.5 + AB_eps) * dtr[c * 3 + tau] - (0.5 + AB_eps) * dtr[c * 3 + taum1]) * maskT[c];
+}

@@ -214,3 +214,31 @@ def set_eke_diffusivities(st, sum_variant=1):
     if not on:
         return {"K_gm": out["K_gm"], "K_iso": out["K_iso"]}
     return out
+
+
+def advect_tracer(st, tracer, lev=None):
+    """thermodynamics.advect_tracer(state, st[tracer][..., lev]) (veros/core/thermodynamics.py:10-40); returns dtr."""
+    N, M, nz = st["maskT"].shape
+    lev = int(st["tau"]) if lev is None else int(lev)
+    dtr = np.zeros((N, M, nz))
+    args = [_f64(st[tracer]), _f64(st["u"]), _f64(st["v"]), _f64(st["w"])] + [_u8(st[m]) for m in ("maskT", "maskU", "maskV", "maskW")]
+    args += [_f64(st[m]) for m in ("dxt", "dyt", "dzt", "cost", "cosu")] + [dtr]
+    lib().oracle_advect_tracer(ctypes.c_int32(N), ctypes.c_int32(M), ctypes.c_int32(nz),
+                               ctypes.c_int32(int(bool(st["enable_superbee_advection"]))), ctypes.c_int32(int(st["tau"])),
+                               ctypes.c_int32(lev), ctypes.c_double(float(st["dt_tracer"])), *[_p(a) for a in args])
+    return dtr
+
+
+def advect_tempsalt(st):
+    """advect_temperature, advect_salinity (thermodynamics.py:43-62) and the Adams-Bashforth step (:223-245), in place
+    on st["dtemp"|"dsalt"][..., tau] and st["temp"|"salt"][..., taup1]."""
+    N, M, nz = st["maskT"].shape
+    tau, taup1 = int(st["tau"]), int(st["taup1"])
+    taum1 = int(st.get("taum1", 3 - tau - taup1))
+    for tr, d in (("temp", "dtemp"), ("salt", "dsalt")):
+        st[tr], st[d] = _f64(st[tr]).copy(), _f64(st[d]).copy()
+        st[d][..., tau] = advect_tracer(st, tr)
+        lib().oracle_adams_bashforth(ctypes.c_int32(N), ctypes.c_int32(M), ctypes.c_int32(nz), ctypes.c_int32(tau),
+                                     ctypes.c_int32(taup1), ctypes.c_int32(taum1), ctypes.c_double(float(st["dt_tracer"])),
+                                     ctypes.c_double(float(st["AB_eps"])), _p(st[tr]), _p(st[d]), _p(_u8(st["maskT"])))
+    return st

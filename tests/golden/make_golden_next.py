@@ -10,6 +10,8 @@ implementation (runs only in the build container: imports veros from /root/refer
   K_diss_v.  Random kappaM makes dgtsv interchange rows in many columns.
 * ``sf_*``    isoneutral_diag_streamfunction_kernel (veros/core/isoneutral/isoneutral.py:232-258): inputs K_gm,
   Ai_ez, Ai_nz, B1_gm, B2_gm; outputs B1_gm, B2_gm.
+* ``adv_*``   advect_tracer (veros/core/thermodynamics.py:10-40, superbee and 2nd-order fluxes of advection.py),
+  advect_temperature / advect_salinity and the Adams-Bashforth step (:223-245).
 * ``eke_*``   set_eke_diffusivities_kernel (veros/core/eke.py:34-85), both branches (enable_eke on / off).
 """
 import os
@@ -97,8 +99,39 @@ def eke_case(name, seed, **extra):
     save(name, out)
 
 
+def advection_case(name, seed, **extra):
+    """advect_temperature + advect_salinity (thermodynamics.py:43-62 -> advect_tracer :10-40) and the Adams-Bashforth
+    step of :223-245 (re-stated here from the reference's own expressions, which sit at the end of
+    advect_temp_salt_enthalpy behind the energy diagnostics)."""
+    from veros.core import thermodynamics
+
+    state = random_state(seed, **extra)
+    vs, st = state.variables, state.settings
+    out = {}
+    for k in ("temp", "salt", "dtemp", "dsalt", "u", "v", "w", "maskT", "maskU", "maskV", "maskW", "dxt", "dyt", "dzt",
+              "cost", "cosu"):
+        out["in__" + k] = np.array(getattr(vs, k))
+    for k in ("tau", "taup1", "taum1"):
+        out["in__" + k] = np.int32(getattr(vs, k))
+    for k in ("nx", "ny", "nz", "dt_tracer", "AB_eps", "enable_superbee_advection"):
+        out["set__" + k] = np.asarray(getattr(st, k))
+    out["out__dtr_temp"] = np.array(thermodynamics.advect_tracer(state, vs.temp[..., vs.tau]))
+    vs.update(thermodynamics.advect_temperature(state))
+    vs.update(thermodynamics.advect_salinity(state))
+    for tr, d in (("temp", "dtemp"), ("salt", "dsalt")):
+        x, dx = getattr(vs, tr), getattr(vs, d)
+        x[:, :, :, vs.taup1] = (x[:, :, :, vs.tau] + st.dt_tracer * ((1.5 + st.AB_eps) * dx[:, :, :, vs.tau]
+                                                                    - (0.5 + st.AB_eps) * dx[:, :, :, vs.taum1]) * vs.maskT)
+        out["out__" + tr], out["out__" + d] = np.array(x), np.array(dx)
+    save(name, out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["fric", "sf", "eke"]
+    which = sys.argv[1:] or ["fric", "sf", "eke", "adv"]
+    if "adv" in which:
+        advection_case("adv_superbee_10x8x7", 71, nx=10, ny=8, nz=7, enable_superbee_advection=True)
+        advection_case("adv_superbee_6x5x2_cyclic", 72, nx=6, ny=5, nz=2, enable_superbee_advection=True, enable_cyclic_x=True)
+        advection_case("adv_2nd_9x7x5", 73, nx=9, ny=7, nz=5, enable_superbee_advection=False)
     if "fric" in which:
         friction_case("fric_rand_10x8x7", 41, nx=10, ny=8, nz=7)
         friction_case("fric_rand_6x5x12_cyclic", 42, nx=6, ny=5, nz=12, enable_cyclic_x=True)

@@ -164,3 +164,53 @@ def test_set_eke_diffusivities_vs_oracle(nz, dev):
     got = gs.to_numpy(list(ref))
     for k in ref:
         assert np.array_equal(got[k], ref[k]), k
+
+
+# ---------------------------------------------------------------------------------- advect_tempsalt (+ Adams-Bashforth)
+ADV_OUT = ("temp", "salt", "dtemp", "dsalt")
+
+
+@pytest.mark.parametrize("name", helpers.io_golden_names("adv_"))
+def test_advect_tempsalt_bitexact_vs_reference_golden(name, dev):
+    from veros_b200 import thermodynamics
+
+    st, out = helpers.load_io_golden(name)
+    gs = gpu_state(st, dev)
+    res = thermodynamics.advect_tempsalt(gs)
+    assert res._fields == ADV_OUT
+    got = gs.to_numpy(list(ADV_OUT))
+    for k in ADV_OUT:
+        assert np.array_equal(got[k], out[k]), k
+    # tendencies only (advect_temperature / advect_salinity without the time step)
+    gs = gpu_state(st, dev)
+    thermodynamics.advect_tempsalt(gs, adams_bashforth=False)
+    got = gs.to_numpy(list(ADV_OUT))
+    assert np.array_equal(got["dtemp"][..., int(st["tau"])], out["dtr_temp"])
+    assert np.array_equal(got["temp"], st["temp"]) and np.array_equal(got["dsalt"], out["dsalt"])
+
+
+@pytest.mark.parametrize("shape,superbee", [((48, 40, 50), True), ((48, 40, 50), False), ((20, 18, 115), True),
+                                            ((9, 6, 1), True), ((150, 7, 2), True)])
+def test_advect_tempsalt_vs_oracle(shape, superbee, dev):
+    from oracle import oracle
+    from veros_b200 import synthetic, thermodynamics
+
+    nx, ny, nz = shape
+    base = synthetic.random_state(nx, ny, max(nz, 2), seed=5)
+    rng = np.random.default_rng(6)
+    N, M = nx + 4, ny + 4
+    st = {k: base[k] for k in ("dxt", "dyt", "cost", "cosu", "tau", "taup1", "dt_tracer")}
+    st["cosu"] = np.cos(np.linspace(-1.2, 1.2, M))  # not all ones: the north flux carries cosu
+    st["cost"] = np.cos(np.linspace(-1.15, 1.15, M))
+    st["kbot"] = np.minimum(base["kbot"], nz).astype(np.int32)
+    st["maskT"], st["maskU"], st["maskV"], st["maskW"] = synthetic.masks_from_kbot(st["kbot"], nz, False)
+    st["dzt"] = base["dzt"][:nz].copy()
+    st["temp"], st["salt"], st["dtemp"], st["dsalt"] = rng.standard_normal((4, N, M, nz, 3))
+    st["u"], st["v"], st["w"] = rng.standard_normal((3, N, M, nz, 3)) * np.array([1.0, 1.0, 1e-3])[:, None, None, None, None]
+    st["AB_eps"], st["enable_superbee_advection"] = 0.1, superbee
+    ref = oracle.advect_tempsalt(copy_state(st))
+    gs = gpu_state(st, dev)
+    thermodynamics.advect_tempsalt(gs)
+    got = gs.to_numpy(list(ADV_OUT))
+    for k in ADV_OUT:
+        assert np.array_equal(got[k], ref[k]), k

@@ -176,3 +176,14 @@ def test_oracle_set_eke_diffusivities_bitexact(name):
     assert set(got) == set(out)
     for k in out:
         assert np.array_equal(got[k], out[k]), k
+
+
+@pytest.mark.parametrize("name", helpers.io_golden_names("adv_"))
+def test_oracle_advect_tempsalt_bitexact(name):
+    """advect_tracer with the superbee / 2nd-order fluxes (thermodynamics.py:10-40, advection.py:8-115),
+    advect_temperature / advect_salinity and the Adams-Bashforth step (:223-245): bit for bit."""
+    st, out = helpers.load_io_golden(name)
+    assert np.array_equal(oracle.advect_tracer(helpers.copy_state(st), "temp"), out["dtr_temp"])
+    got = oracle.advect_tempsalt(helpers.copy_state(st))
+    for k in ("temp", "salt", "dtemp", "dsalt"):
+        assert np.array_equal(got[k], out[k]), k

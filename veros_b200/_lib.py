@@ -21,6 +21,7 @@ OPS = (
     "veros_b200_implicit_vert_friction_f64",
     "veros_b200_iso_diag_streamfunction_f64",
     "veros_b200_set_eke_diffusivities_f64",
+    "veros_b200_advect_tempsalt_f64",
 )
 HELPERS = (
     "veros_b200_iso_pre_workspace_bytes",
@@ -81,6 +82,12 @@ class EkeDescriptor(ctypes.Structure):
                                                "K_gm_0", "K_iso_0")]
 
 
+class AdvectDescriptor(ctypes.Structure):
+    _fields_ = [("nx_tot", ctypes.c_int32), ("ny_tot", ctypes.c_int32), ("nz", ctypes.c_int32),
+                ("flags", ctypes.c_int32), ("dt_tracer", ctypes.c_double), ("AB_eps", ctypes.c_double)]
+
+
+ADVECT_SUPERBEE, ADVECT_NO_AB = 1, 2
 HAS_B_EDGE, HAS_D_EDGE = 1, 2
 FLAG_SKEW = 1
 FLAG_NO_WEST_RING, FLAG_NO_EAST_RING = 2, 4
@@ -136,7 +143,7 @@ def lib():
     if L.veros_b200_abi_version() != ABI_VERSION:
         raise RuntimeError("libveros_b200.so ABI version mismatch; rebuild with `python -m veros_b200.build --force`")
     for which, cls in enumerate((TridiagDescriptor, SolveDescriptor, IsoDescriptor, VmixDescriptor, ColumnDescriptor,
-                                 EkeDescriptor)):
+                                 EkeDescriptor, AdvectDescriptor)):
         if L.veros_b200_descriptor_size(which) != ctypes.sizeof(cls):
             raise RuntimeError(f"descriptor layout mismatch for {cls.__name__}")
     _lib = L

@@ -23,6 +23,7 @@ SOURCES = {
     "iso_diffusion.cu": [],
     "iso_mega.cu": [],
     "next_ops.cu": [],
+    "advect.cu": [],
     "halo.cu": [],
     "vertmix.cu": [],
 }

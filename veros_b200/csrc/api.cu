@@ -421,6 +421,18 @@ void veros_b200_set_eke_diffusivities_f64(void* stream, void** B, const char* op
     launch_set_eke_diffusivities((cudaStream_t)stream, d, B);
 }
 
+void veros_b200_advect_tempsalt_f64(void* stream, void** B, const char* opaque, size_t len) {
+    begin_call();
+    const auto* d = unpack<VerosB200AdvectDescriptor>(opaque, len, "advect_tempsalt: bad descriptor");
+    if (!d) return;
+    if (d->nx_tot < 5 || d->ny_tot < 5 || d->nz < 1 || !(d->dt_tracer > 0.0))
+        return set_error(VEROS_B200_ERR_BAD_ARGUMENT, "advect_tempsalt: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n3 = (size_t)d->nx_tot * d->ny_tot * d->nz;
+    for (int q = 0; q < 4; ++q) alias_copy(s, B[19 + q], B[q], n3 * 24);
+    launch_advect_tempsalt(s, d, B);
+}
+
 void veros_b200_profile_events(void** events, int n) {
     g_prof_events = reinterpret_cast<cudaEvent_t*>(events);
     g_prof_n = events ? n : 0;
@@ -472,6 +484,7 @@ extern "C" size_t veros_b200_descriptor_size(int which) {
     case 3: return sizeof(VerosB200VmixDescriptor);
     case 4: return sizeof(VerosB200ColumnDescriptor);
     case 5: return sizeof(VerosB200EkeDescriptor);
+    case 6: return sizeof(VerosB200AdvectDescriptor);
     default: return 0;
     }
 }

@@ -117,6 +117,7 @@ void launch_vertmix(cudaStream_t s, const VmixArgs& a);
 void launch_implicit_vert_friction(cudaStream_t s, int N, int M, int nz, double dt_mom, void** B);
 void launch_diag_streamfunction(cudaStream_t s, int N, int M, int nz, void** B);
 void launch_set_eke_diffusivities(cudaStream_t s, const VerosB200EkeDescriptor* d, void** B);
+void launch_advect_tempsalt(cudaStream_t s, const VerosB200AdvectDescriptor* d, void** B);  // advect.cu
 // the fused persistent step kernel (iso_mega.cu)
 size_t mega_ring_doubles(int N, int M, int nz, int eos, int energy);
 size_t mega_sync_doubles(int N);

@@ -21,7 +21,7 @@ F64_3D = ("K_iso", "K_gm", "K_11", "K_22", "K_33", "dtemp_iso", "dsalt_iso", "P_
           # neighbours of the path (friction.py, eke.py, isoneutral_diag_streamfunction)
           "kappaM", "du_mix", "dv_mix", "K_diss_v", "B1_gm", "B2_gm", "L_rhines", "eke_len", "sqrteke")
 F64_2D = ("forc_temp_surface", "forc_salt_surface", "area_v", "area_t", "coriolis_t", "beta", "L_rossby")
-F64_4D = ("temp", "salt", "int_drhodT", "int_drhodS", "u", "v", "Nsqr", "eke")
+F64_4D = ("temp", "salt", "int_drhodT", "int_drhodS", "u", "v", "Nsqr", "eke", "w", "dtemp", "dsalt")
 F64_5D = ("Ai_ez", "Ai_nz", "Ai_bx", "Ai_by")
 MASKS = ("maskT", "maskU", "maskV", "maskW")
 METRICS_X = ("dxt", "dxu")
@@ -29,14 +29,14 @@ METRICS_Y = ("dyt", "dyu", "cost", "cosu")
 METRICS_Z = ("dzt", "dzw", "zt")
 SETTINGS = ("eq_of_state_type", "enable_conserve_energy", "K_iso_steep", "iso_slopec", "iso_dslope",
             "dt_tracer", "grav", "rho_0")
-EXTRA_SETTINGS = ("dt_mom", "enable_eke", "enable_eke_isopycnal_diffusion", "pi", "eke_lmin", "eke_cross", "eke_crhin",
+EXTRA_SETTINGS = ("AB_eps", "enable_superbee_advection", "dt_mom", "enable_eke", "enable_eke_isopycnal_diffusion", "pi", "eke_lmin", "eke_cross", "eke_crhin",
                   "eke_k_max", "eke_c_k", "K_gm_0", "K_iso_0")
 OPTIONAL = ("K_gm", "P_diss_skew", "int_drhodT", "int_drhodS", "P_diss_iso",
             # vertmix_tempsalt (veros_b200/thermodynamics.py)
             "kappaH", "dtemp_vmix", "dsalt_vmix", "forc_temp_surface", "forc_salt_surface",
             # friction.py, eke.py, isoneutral_diag_streamfunction
             "kappaM", "du_mix", "dv_mix", "K_diss_v", "B1_gm", "B2_gm", "L_rhines", "eke_len", "sqrteke", "area_v", "area_t",
-            "coriolis_t", "beta", "L_rossby", "u", "v", "Nsqr", "eke")
+            "coriolis_t", "beta", "L_rossby", "u", "v", "Nsqr", "eke", "w", "dtemp", "dsalt")
 
 
 def KernelOutput(**kwargs):
@@ -88,8 +88,8 @@ class IsoState:
                 put(name, np.asarray(st[name]).astype(np.uint8), np.uint8)
         if "kbot" in st or strict:
             put("kbot", st["kbot"], np.int32)
-        for name in ("tau", "taup1"):
-            if name in st or strict:
+        for name in ("tau", "taup1", "taum1"):
+            if name in st or (strict and name != "taum1"):
                 put(name, np.array([int(st[name])]), np.int32)
                 setattr(vs, name + "_host", int(st[name]))  # host copy for plumbing (halo packing)
         settings = SimpleNamespace(**{k: st[k] for k in SETTINGS if strict or k in st})

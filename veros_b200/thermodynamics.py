@@ -46,6 +46,38 @@ def vertmix_tempsalt(state, group=None):
     return KernelOutput(dtemp_vmix=vs.dtemp_vmix, temp=vs.temp, dsalt_vmix=vs.dsalt_vmix, salt=vs.salt)
 
 
+ADVECT_NEEDS = ("temp", "salt", "dtemp", "dsalt", "tau", "taup1", "u", "v", "w", "maskT", "maskU", "maskV", "maskW", "dxt", "dyt",
+                "dzt", "cost", "cosu")
+
+
+def advect_tempsalt(state, adams_bashforth=True):
+    """advect_temperature + advect_salinity (veros/core/thermodynamics.py:43-62, i.e. d{temp,salt}[..., tau] =
+    advect_tracer(...), :10-40) and, unless `adams_bashforth` is False, the Adams-Bashforth step of :223-245 that
+    produces temp/salt[..., taup1] -- one kernel launch for both tracers (csrc/advect.cu), bit-identical to the
+    reference's NumPy backend.  Returns KernelOutput(temp, salt, dtemp, dsalt) like the reference's kernels."""
+    vs, settings = state.variables, state.settings
+    for name in ADVECT_NEEDS:
+        if getattr(vs, name, None) is None:
+            raise ValueError(f"advect_tempsalt needs variable {name}")
+    if not vs.temp.is_cuda:
+        raise RuntimeError("veros_b200 has no CPU path: the state must live on a CUDA device")
+    N, M, nz = settings.nx + 4, settings.ny + 4, settings.nz
+    if tuple(vs.dtemp.shape) != (N, M, nz, 3) or tuple(vs.w.shape) != (N, M, nz, 3):
+        raise ValueError("dtemp / w do not match the grid")
+    if getattr(vs, "taum1", None) is None:  # taum1 = the third time level
+        vs.taum1 = (3 - vs.tau - vs.taup1).to(torch.int32)
+    flags = (_lib.ADVECT_SUPERBEE if getattr(settings, "enable_superbee_advection", False) else 0) | \
+            (0 if adams_bashforth else _lib.ADVECT_NO_AB)
+    desc = _lib.AdvectDescriptor(nx_tot=N, ny_tot=M, nz=nz, flags=flags, dt_tracer=float(settings.dt_tracer),
+                                 AB_eps=float(getattr(settings, "AB_eps", 0.1)))
+    inout = [vs.temp, vs.salt, vs.dtemp, vs.dsalt]
+    operands = inout + [vs.tau, vs.taup1, vs.taum1, vs.u, vs.v, vs.w, vs.maskT, vs.maskU, vs.maskV, vs.maskW, vs.dxt, vs.dyt,
+                        vs.dzt, vs.cost, vs.cosu]
+    _lib.call("veros_b200_advect_tempsalt_f64", [int(t.data_ptr()) for t in operands + inout], desc,
+              torch.cuda.current_stream(state.device).cuda_stream)
+    return KernelOutput(temp=vs.temp, salt=vs.salt, dtemp=vs.dtemp, dsalt=vs.dsalt)
+
+
 class VertmixPlan:
     """The kernel of `vertmix_tempsalt(state)` with the argument marshalling done once (cf.
     isoneutral.StepPlan): one foreign-function call per invocation, no boundary exchange."""
