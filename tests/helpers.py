@@ -12,7 +12,7 @@ KS = ("K_11", "K_22", "K_33")
 
 def golden_names():
     names = (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return sorted(n for n in names if not n.startswith(("vmix_", "fric_", "sf_", "eke_")))
+    return sorted(n for n in names if not n.startswith(("vmix_", "fric_", "sf_", "eke_", "adv_")))
 
 
 def load_golden(name):
