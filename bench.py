@@ -269,6 +269,37 @@ def timed(fn, n):
     return e0.elapsed_time(e1) / n
 
 
+def assemble_on_device(name, nslabs, dev):
+    """IsoState of a whole named grid on `dev`, generated on the host slab by slab (x_offset) so that the host never
+    holds more than one slab: local planes [0, nxl + 4) of slab s are global planes [s nxl, s nxl + nxl + 4)."""
+    import torch
+
+    from veros_b200 import synthetic
+    from veros_b200.state import IsoState
+
+    nxg = synthetic.WORKLOADS[name]["nx"]
+    nxl = nxg // nslabs
+    first = synthetic.make_workload(name, nx=nxl, x_offset=0, nx_global=nxg)
+    N = nxg + 4
+    proto = IsoState.from_numpy(first, dev)
+    full = {}
+    for k, t in vars(proto.variables).items():
+        if hasattr(t, "shape") and t.dim() >= 1 and t.shape[0] == nxl + 4 and k not in ("dyt", "dyu", "cost", "cosu", "dzt", "dzw", "zt"):
+            full[k] = torch.empty((N,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            full[k][:nxl + 4].copy_(t)
+    for s_ in range(1, nslabs):
+        part = IsoState.from_numpy(synthetic.make_workload(name, nx=nxl, x_offset=s_ * nxl, nx_global=nxg), dev)
+        for k in full:
+            full[k][s_ * nxl:s_ * nxl + nxl + 4].copy_(getattr(part.variables, k))
+        del part
+    for k, t in full.items():
+        setattr(proto.variables, k, t)
+    proto.settings.nx = nxg
+    proto._workspace = None
+    proto.validate()
+    return proto
+
+
 def side_measurements(dev, peak):
     """The other single-GPU configs of BASELINE.json, each the fused step on its own synthetic state (not part of
     `value`): bench_1M (configs[1]), global_4deg through a CUDA graph (configs[2], latency path), the ACC grid
@@ -303,6 +334,24 @@ def side_measurements(dev, peak):
         out[name] = rec
         del states, plans
         torch.cuda.empty_cache()
+    # the strong-scaling grid on ONE GPU (the N = 1 point of BASELINE.json's 0.25 degree config): 83 M cells, 25 GB state,
+    # assembled on the device from sixteen 90-plane slabs of the same generator the multi-GPU ranks use
+    try:
+        big = assemble_on_device("global_025deg", 16, dev)
+        cells = big.settings.nx * big.settings.ny * big.settings.nz
+        plan = isoneutral.StepPlan(big)
+        for _ in range(2):
+            plan()
+        ms = timed(lambda k: plan(), 5)
+        out["global_025deg"] = {"grid": f"{big.settings.nx}x{big.settings.ny}x{big.settings.nz}", "eq_of_state_type": 5,
+                                "ms_per_step": ms, "value": cells / (ms * 1e-3),
+                                "step_roofline_frac": cells * 276 / (ms * 1e-3) / 1e9 / peak,
+                                "note": "one state of 25 GB streamed per step (far larger than L2); the single-GPU point of the "
+                                        "strong-scaling curve that `--gpus N` measures"}
+        del big, plan
+        torch.cuda.empty_cache()
+    except Exception as err:  # e.g. a GPU without the memory
+        out["global_025deg"] = {"error": str(err)}
     # stand-alone solve_implicit: random 70 x 60 x 50 systems as the reference's TDMA benchmark, and a 1 degree sized batch
     rng = np.random.default_rng(17)
     for label, (nx, ny, nz) in (("tdma_benchmark_70x60x50", (70, 60, 50)), ("global_1deg_364x164x115", (364, 164, 115))):
@@ -319,6 +368,61 @@ def side_measurements(dev, peak):
                                           "achieved_gbs": n * SOLVE_BYTES_PER_CELL / (ms * 1e-3) / 1e9,
                                           "frac": n * SOLVE_BYTES_PER_CELL / (ms * 1e-3) / 1e9 / peak,
                                           "note": "native z-contiguous layout, dgtsv replay incl. pivoting, output allocation included"}
+    return out
+
+
+def neighbour_ops(state, dev, peak, cells):
+    """Device time of the SURVEY.md 8f rank 3 / rank 4 ops on the benchmark grid (random inputs of the right shapes;
+    not part of `value`): implicit_vert_friction, advect_tempsalt (+ Adams-Bashforth), set_eke_diffusivities,
+    isoneutral_diag_streamfunction, each with its algorithmic bytes per cell and fraction of the measured HBM peak."""
+    import torch
+
+    from veros_b200 import eke, friction, isoneutral, thermodynamics
+
+    vs, st = state.variables, state.settings
+    N, M, nz = st.nx + 4, st.ny + 4, st.nz
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(11)
+    r = lambda *shape, scale=1.0: torch.randn(shape, dtype=torch.float64, device=dev, generator=gen) * scale
+    extra = dict(u=r(N, M, nz, 3), v=r(N, M, nz, 3), w=r(N, M, nz, 3, scale=1e-4), kappaM=r(N, M, nz).abs_() * 1e-2,
+                 du_mix=r(N, M, nz), dv_mix=r(N, M, nz), K_diss_v=r(N, M, nz), area_t=r(N, M).abs_() + 1.0,
+                 area_v=r(N, M).abs_() + 1.0, dtemp=r(N, M, nz, 3, scale=1e-6), dsalt=r(N, M, nz, 3, scale=1e-7),
+                 Nsqr=r(N, M, nz, 3, scale=1e-5), eke=r(N, M, nz, 3, scale=1e-2), coriolis_t=r(N, M, scale=1e-4),
+                 beta=r(N, M).abs_() * 2e-11, B1_gm=r(N, M, nz), B2_gm=r(N, M, nz))
+    saved = {k: getattr(vs, k, None) for k in extra}
+    saved_tr = (vs.temp.clone(), vs.salt.clone())
+    for k, v_ in extra.items():
+        setattr(vs, k, v_)
+    st.dt_mom, st.AB_eps, st.enable_superbee_advection = float(st.dt_tracer), 0.1, True
+    st.enable_eke, st.enable_eke_isopycnal_diffusion = True, True
+    st.pi, st.eke_lmin, st.eke_cross, st.eke_crhin, st.eke_k_max, st.eke_c_k = 3.141592653589793, 100.0, 2.0, 1.0, 1e4, 0.4
+    st.K_gm_0, st.K_iso_0 = 1000.0, 1000.0
+    kg, ki = vs.K_gm.clone(), vs.K_iso.clone()
+    ops = {
+        "implicit_vert_friction": (lambda: friction.implicit_vert_friction(state), 90,
+                                   "veros/core/friction.py:92-205, coefficient assembly fused into two dgtsv solves (3 launches)"),
+        "advect_tempsalt_adams_bashforth": (lambda: thermodynamics.advect_tempsalt(state), 92,
+                                            "thermodynamics.py:10-62,223-245 with superbee fluxes, both tracers, one launch"),
+        "set_eke_diffusivities": (lambda: eke.set_eke_diffusivities_kernel(state), 57, "veros/core/eke.py:34-85, one launch"),
+        "isoneutral_diag_streamfunction": (lambda: isoneutral.isoneutral_diag_streamfunction(state), 88,
+                                           "isoneutral.py:232-258, one launch"),
+    }
+    out = {}
+    for name_, (fn, nbytes, note) in ops.items():
+        for _ in range(3):
+            fn()
+        ms = timed(lambda k: fn(), 10)
+        gbs = cells * nbytes / (ms * 1e-3) / 1e9
+        out[name_] = {"ms": ms, "algorithmic_bytes_per_cell": nbytes, "achieved_gbs": gbs, "frac": gbs / peak, "note": note}
+    vs.K_gm.copy_(kg)
+    vs.K_iso.copy_(ki)
+    vs.temp.copy_(saved_tr[0])
+    vs.salt.copy_(saved_tr[1])
+    for k, v_ in saved.items():
+        if v_ is None:
+            delattr(vs, k)
+        else:
+            setattr(vs, k, v_)
     return out
 
 
@@ -630,6 +734,8 @@ def main():
                                      "achieved_gbs": cells * VMIX_BYTES / (vmix_ms * 1e-3) / 1e9,
                                      "frac": cells * VMIX_BYTES / (vmix_ms * 1e-3) / 1e9 / peak,
                                      "note": "the step after the path (SURVEY.md 8f rank 1), one kernel, not part of `value`"}}
+    if world == 1 and not args.profile:
+        next_ops.update(neighbour_ops(states[0], dev, peak, cells))
     if args.profile:
         if rank == 0:
             sampler.stop()

@@ -251,13 +251,40 @@ def make_replacements():
         salt = update(salt, at[..., vs.taup1], utilities.enforce_boundaries(salt[..., vs.taup1], st.enable_cyclic_x))
         return KernelOutput(dtemp_vmix=dtemp_vmix, temp=temp, dsalt_vmix=dsalt_vmix, salt=salt)
 
-    return dict(vertmix_tempsalt=vertmix_tempsalt, isoneutral_diffusion_pre=isoneutral_diffusion_pre, isoneutral_diffusion=isoneutral_diffusion,
+    @veros_kernel
+    def isoneutral_fused_step(state):
+        """thermodynamics.py:430-432 as ONE custom call (veros_b200_iso_step_f64); returns all twelve arrays."""
+        from .facade import STEP_OUTPUTS
+
+        vs, st = state.variables, state.settings
+        energy = st.enable_conserve_energy
+        dummy = jnp.zeros((1,), dtype=vs.temp.dtype)
+        inout = [vs.temp, vs.salt, vs.dtemp_iso, vs.dsalt_iso, vs.P_diss_iso if energy else dummy]
+        inout += [getattr(vs, n) for n in _PRE_OUT]
+        ops = inout + [_i32(vs.tau), _i32(vs.taup1), vs.K_iso, _u8(vs.maskT), _u8(vs.maskU), _u8(vs.maskV), _u8(vs.maskW),
+                       vs.kbot.astype(jnp.int32)]
+        ops += [getattr(vs, n) for n in _METRICS] + [vs.zt]
+        ops += [vs.int_drhodT if energy else dummy, vs.int_drhodS if energy else dummy]
+        out = P["step"].bind(*ops, descriptor=bytes(_iso_descriptor(state)))
+        res = dict(zip(STEP_OUTPUTS, out[:12]))
+        if not energy:
+            res.pop("P_diss_iso")
+        return KernelOutput(**res)
+
+    return dict(isoneutral_fused_step=isoneutral_fused_step,
+                vertmix_tempsalt=vertmix_tempsalt, isoneutral_diffusion_pre=isoneutral_diffusion_pre, isoneutral_diffusion=isoneutral_diffusion,
                 isoneutral_skew_diffusion=isoneutral_skew_diffusion, solve_implicit=solve_implicit,
                 solve_tridiagonal=solve_tridiagonal)
 
 
-def install():
-    """Idempotent; re-apply after anything reloads veros.core (test/pyom_consistency/conftest.py:21-32)."""
+def install(fused=True):
+    """Idempotent; re-apply after anything reloads veros.core (test/pyom_consistency/conftest.py:21-32).
+
+    The three functions of the call surface are rebound on `veros.core.isoneutral` (every caller sees them).  With
+    `fused` (default) the model's own call site, veros/core/thermodynamics.py:430-432, additionally goes through
+    `veros_b200.facade`: its `isoneutral` module global becomes a stand-in whose `isoneutral_diffusion_pre` is the ONE
+    fused step op and whose `isoneutral_diffusion` has nothing left to do, so a model step runs the fused kernels
+    (what bench.py times) instead of three separate custom calls."""
     from veros import runtime_settings as rs
 
     if rs.backend != "jax" or rs.device != "gpu":
@@ -280,4 +307,10 @@ def install():
     import veros.core.thermodynamics as thermodynamics
 
     thermodynamics.vertmix_tempsalt = r["vertmix_tempsalt"]  # looked up as a module global at :440
+    from . import facade
+
+    if fused:
+        facade.install_facade(thermodynamics, iso_pkg, r["isoneutral_fused_step"])
+    else:
+        facade.uninstall_facade(thermodynamics, iso_pkg)
     return r
