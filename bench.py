@@ -512,7 +512,8 @@ def main():
     ap.add_argument("--profile", action="store_true",
                     help="only warm-up + timed steps + per-kernel pass (for ncu launch lists): no e2e, cpu or extra legs")
     ap.add_argument("--overlap", default="auto", choices=["auto", "on", "off"],
-                    help="N > 1: hide the halo exchange behind interior compute (auto: slabs of >= 3 M cells)")
+                    help="N > 1: hide the halo exchange behind interior compute (auto: only with --halo nccl on slabs of "
+                         ">= 3 M cells; the peer-memory exchange is too short to be worth the extra strip passes)")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3)
@@ -586,7 +587,11 @@ def main():
     states = [probe] + [IsoState.from_numpy(st, dev) for _ in range(replicas - 1)]
 
     plans = [isoneutral.StepPlan(s) for s in states]  # argument marshalling done once, as under XLA
-    overlap = world > 1 and (args.overlap == "on" or (args.overlap == "auto" and cells >= 3_000_000))
+    # Overlap (boundary strips first, exchange hidden behind the interior) pays when the exchange is slow relative to
+    # the step: measured on 2 GPUs, 0.25 degree strong scaling (profiles/r02_scaling.md): peer-memory exchange after
+    # the step 7.23 ms/step (98 % efficient) vs overlapped 8.19 ms (the two extra strip passes cost more than the
+    # ~20 us exchange they hide); with pack + NCCL + unpack on >= 3 M-cell slabs the overlap wins (round 1).
+    overlap = world > 1 and (args.overlap == "on" or (args.overlap == "auto" and args.halo == "nccl" and cells >= 3_000_000))
 
     def build_exchange(halo):
         steppers_ = [decomp.OverlappedStepper(s, cyclic=cyclic, halo=halo) for s in states] if overlap else None
