@@ -426,7 +426,7 @@ def neighbour_ops(state, dev, peak, cells):
     return out
 
 
-def seam_parity(args, name, nxl, rank, world, dev, cyclic, halo, overlap):
+def seam_parity(args, name, kw, xb, nxg, rank, world, dev, cyclic, halo, overlap):
     """One step of fresh slab states on all ranks (same stepper class as the timed run), then ranks 0 and 1
     compare the planes either side of their common boundary -- the exchanged ghost planes included -- with a
     single-GPU run of those planes (a 16-plane slab around the seam generated with the same x_offset mechanism).
@@ -438,8 +438,7 @@ def seam_parity(args, name, nxl, rank, world, dev, cyclic, halo, overlap):
     from veros_b200 import decomp, isoneutral, synthetic
     from veros_b200.state import IsoState
 
-    nxg = nxl * world
-    st = synthetic.make_workload(name, nx=nxl, x_offset=rank * nxl, nx_global=nxg)
+    st = synthetic.make_workload(name, **kw)  # this rank's slab; `xb` = first interior plane of rank 1 (global index)
     lvl = int(st["taup1"])
     gs = IsoState.from_numpy(st, dev)
     if overlap:
@@ -467,7 +466,7 @@ def seam_parity(args, name, nxl, rank, world, dev, cyclic, halo, overlap):
         dist.recv(theirs, src=1)
         mine = torch.stack([pick(getattr(vs, n), slice(vs.K_33.shape[0] - 2 - H, vs.K_33.shape[0])) for n in names])
         # single-GPU reference: interior planes [nxl - H, nxl + H) of the global grid as one small slab
-        seam = synthetic.make_workload(name, nx=2 * H, x_offset=nxl - H, nx_global=nxg)
+        seam = synthetic.make_workload(name, nx=2 * H, x_offset=xb - H, nx_global=nxg)
         ss = IsoState.from_numpy(seam, dev)
         isoneutral.isoneutral_step(ss)
         torch.cuda.synchronize()
@@ -486,7 +485,7 @@ def seam_parity(args, name, nxl, rank, world, dev, cyclic, halo, overlap):
         result = {"bit_identical": bool(ok), "fields": worst,
                   "checked": f"one step on fresh slabs; {H} interior planes either side of the rank 0 / rank 1 boundary and the "
                              f"exchanged ghost planes of temp/salt[taup1] against a single-GPU step of global planes "
-                             f"[{nxl - H}, {nxl + H})"}
+                             f"[{xb - H}, {xb + H})"}
     dist.barrier()
     return result
 
@@ -509,6 +508,9 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="N > 1: strong = the named grid is split over the ranks (default, BASELINE.json's 0.25 degree "
                          "config); weak = every rank gets a slab of the named size")
+    ap.add_argument("--decomp", default="balanced", choices=["balanced", "even"],
+                    help="N > 1, strong scaling: x-slab cuts that equalise the cost per rank (default) or equal widths as the "
+                         "reference's decomposition (veros/distributed.py:124-128)")
     ap.add_argument("--profile", action="store_true",
                     help="only warm-up + timed steps + per-kernel pass (for ncu launch lists): no e2e, cpu or extra legs")
     ap.add_argument("--overlap", default="auto", choices=["auto", "on", "off"],
@@ -568,10 +570,19 @@ def main():
         else:
             nxl = synthetic.WORKLOADS[name]["nx"]
             if scaling == "strong":
-                if nxl % world:
-                    raise SystemExit(f"--scaling strong: nx = {nxl} is not divisible by {world} ranks")
-                nxl //= world
-            kw = dict(nx=nxl, x_offset=rank * nxl, nx_global=nxl * world)  # one consistent global state
+                # one consistent global state cut into x-slabs; by default the cuts equalise the per-slab COST (wet cells
+                # + 0.34 x dry cells), not the width: continents make equal-width slabs unequal (scaling_breakdown)
+                nxg = nxl
+                if args.decomp == "balanced":
+                    bounds = decomp.balanced_slab_bounds(synthetic.analytic_plane_costs(name), world)
+                else:
+                    bounds = [decomp.slab_bounds(nxg, world, r) for r in range(world)]
+                x0, x1 = bounds[rank]
+                kw = dict(nx=x1 - x0, x_offset=x0, nx_global=nxg)
+            else:
+                nxg = nxl * world
+                bounds = [(r * nxl, (r + 1) * nxl) for r in range(world)]
+                kw = dict(nx=nxl, x_offset=rank * nxl, nx_global=nxg)
     st = synthetic.make_workload(name, **kw)
     nx, ny, nz = st["nx"], st["ny"], st["nz"]
     cells = nx * ny * nz
@@ -634,7 +645,41 @@ def main():
     launches = _lib.launch_count() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
-    value = world * cells * args.steps / (ms_total * 1e-3)
+    total_cells = cells if world == 1 else (world * cells if name == "bench_1M" else nxg * ny * nz)
+    value = total_cells * args.steps / (ms_total * 1e-3)
+
+    # ---- N > 1: where the step time goes -- compute alone on every rank (load balance) and the exchange alone ----
+    scaling_diag = None
+    if world > 1:
+        nrep = min(args.steps, 10)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for k in range(nrep):
+            plans[k % replicas]()
+        c1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([c0.elapsed_time(c1) / nrep], dtype=torch.float64, device=dev)
+        allc = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        x_ms = None
+        if exchanges is not None:
+            barrier()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record()
+            for k in range(nrep):
+                exchanges[k % replicas]()
+            x1.record()
+            barrier()
+            x_ms = max_over_ranks(x0.elapsed_time(x1) / nrep)
+        wet = float(st["maskT"][2:-2, 2:-2].mean())
+        wt = torch.tensor([wet], dtype=torch.float64, device=dev)
+        allw = [torch.zeros_like(wt) for _ in range(world)]
+        dist.all_gather(allw, wt)
+        scaling_diag = {"compute_only_ms_per_rank": [round(float(t.item()), 4) for t in allc],
+                        "exchange_only_ms": x_ms, "wet_cell_fraction_per_rank": [round(float(t.item()), 3) for t in allw],
+                        "note": "step time = slowest rank's compute + exchange + hand-shake skew; equal-width x-slabs of a grid "
+                                "with continents are not equally expensive"}
 
     # ---- per-kernel times INSIDE the fused call: the library records the caller's CUDA events between its
     # kernels (veros_b200_profile_events): [0] start, [1] before / [2] after the slope+flux kernel, [3] end
@@ -755,7 +800,28 @@ def main():
     torch.cuda.empty_cache()
     parity = None
     if world > 1 and name != "bench_1M":
-        parity = seam_parity(args, name, nx, rank, world, dev, cyclic, args.halo, overlap)
+        parity = seam_parity(args, name, kw, bounds[0][1], nxg, rank, world, dev, cyclic, args.halo, overlap)
+
+    # ---- strong scaling: the SAME grid on one GPU (rank 0 alone, the others wait), so that the line carries its own
+    # single-GPU reference point -------------------------------------------------------------------------------------
+    one_gpu = None
+    if world > 1 and scaling == "strong" and not args.no_extra:
+        if rank == 0:
+            try:
+                del states[:], plans[:]
+                torch.cuda.empty_cache()
+                big = assemble_on_device(name, 16 if nxg % 16 == 0 else 1, dev)
+                plan = isoneutral.StepPlan(big)
+                for _ in range(2):
+                    plan()
+                ms1 = timed(lambda k: plan(), 5)
+                one_gpu = {"ms_per_step": ms1, "value": nxg * ny * nz / (ms1 * 1e-3),
+                           "note": f"the whole {nxg}x{ny}x{nz} grid on rank 0's GPU alone, same kernels, no exchange"}
+                del big, plan
+                torch.cuda.empty_cache()
+            except Exception as err:
+                one_gpu = {"error": str(err)}
+        dist.barrier()
 
     # ---- end to end: host buffers in, host buffers out ----------------------------------------------
     hs = None
@@ -776,7 +842,7 @@ def main():
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         clocks = sampler.stop() if rank == 0 else None  # sampled from warm-up to here (all under load)
-        e2e = {"value": world * cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes,
+        e2e = {"value": total_cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes,
                "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
                "note": "HostStepper.step(): pinned host -> device copies of the step's inputs, the fused step, device -> host "
                        "copies of all twelve outputs, slab-pipelined over three streams" +
@@ -803,7 +869,9 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": name, "nx": nx, "ny": ny, "nz": nz, "cells_per_gpu": cells,
-                "global_grid": f"{nx * world if (world > 1 and name != 'bench_1M') else nx}x{ny}x{nz}",
+                "global_grid": f"{nxg if (world > 1 and name != 'bench_1M') else nx}x{ny}x{nz}",
+                "slab_widths": [b - a for a, b in bounds] if (world > 1 and name != "bench_1M") else None,
+                "decomposition": (args.decomp + " x-slabs") if (world > 1 and scaling == "strong") else "even x-slabs",
                 "eq_of_state_type": int(st["eq_of_state_type"]), "enable_conserve_energy": energy,
                 "parallelism": f"x-slabs x{world}" + (((" + ring halo exchange of temp/salt[taup1] by peer-memory stores over NVLink"
                                                         if args.halo == "peer" else " + NCCL ring halo exchange of temp/salt[taup1]") +
@@ -818,6 +886,10 @@ def main():
         }
         if parity is not None:
             line["multi_gpu_parity"] = parity
+        if scaling_diag is not None:
+            line["scaling_breakdown"] = scaling_diag
+        if one_gpu is not None:
+            line["one_gpu_same_grid"] = one_gpu
         if extra:
             line["also"] = extra
         emit(line)

@@ -135,3 +135,31 @@ def test_vertmix_wrapper_validates_before_touching_the_library():
     s.variables.kappaH = s.variables.kappaH[:, :, :-1]
     with pytest.raises(ValueError, match="kappaH"):
         s.validate(strict=False)
+
+
+def test_balanced_slab_bounds_equalise_cost_and_respect_min_width():
+    """Unequal-width x-slabs cut by cost (bench.py strong scaling): contiguous, covering, each at least min_width wide,
+    per-slab cost within a few planes' worth of the mean; the 0.25 degree grid's continents make equal widths differ
+    by +-25 %."""
+    from veros_b200 import decomp, synthetic
+
+    costs = synthetic.analytic_plane_costs("global_025deg")
+    assert costs.shape == (1440,) and np.all(costs > 0)
+    for world in (2, 4, 8):
+        b = decomp.balanced_slab_bounds(costs, world)
+        assert b[0][0] == 0 and b[-1][1] == 1440 and all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+        assert all(x1 - x0 >= 8 for x0, x1 in b)
+        share = np.array([costs[x0:x1].sum() for x0, x1 in b]) / costs.sum() * world
+        assert np.abs(share - 1).max() < 0.02
+    even = np.array([costs[r * 180:(r + 1) * 180].sum() for r in range(8)]) / costs.sum() * 8
+    assert even.max() > 1.1 and even.min() < 0.8
+    # degenerate inputs: uniform costs give (almost) equal widths, narrow grids fall back to min_width, too narrow raises
+    assert decomp.balanced_slab_bounds(np.ones(64), 4) == [(0, 16), (16, 32), (32, 48), (48, 64)]
+    lop = decomp.balanced_slab_bounds(np.r_[np.ones(8) * 100, np.ones(24)], 4)
+    assert all(x1 - x0 >= 8 for x0, x1 in lop) and lop[-1][1] == 32
+    with pytest.raises(ValueError):
+        decomp.balanced_slab_bounds(np.ones(20), 4)
+    # the plane costs are those of the state the generator produces (same bathymetry code path)
+    st = synthetic.make_workload("global_4deg")
+    wet = st["maskT"][2:-2, 2:-2].reshape(90, -1).sum(axis=1)
+    assert np.allclose(synthetic.analytic_plane_costs("global_4deg"), wet + 0.34 * (40 * 15 - wet))

@@ -50,7 +50,15 @@ def slab_of(st, x0, nxl):
     return out
 
 
-def _worker(rank, world, port, kind, halo, outdir):
+def bounds_of(kind, even):
+    """Interior x-ranges of the two slabs: equal widths, or the unequal widths a cost-balanced cut produces."""
+    nx = global_state(kind)["nx"] if even else None
+    if even:
+        return [(0, nx // 2), (nx // 2, nx)]
+    return [(0, 12), (12, 32)] if kind == "analytic" else [(0, 9), (9, 24)]
+
+
+def _worker(rank, world, port, kind, halo, outdir, even=True):
     import sys
 
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -66,7 +74,7 @@ def _worker(rank, world, port, kind, halo, outdir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         st = global_state(kind)
-        x0, x1 = decomp.slab_bounds(st["nx"], world, rank)
+        x0, x1 = bounds_of(kind, even)[rank]
         gs = IsoState.from_numpy(slab_of(st, x0, x1 - x0), dev)
         stepper = decomp.OverlappedStepper(gs, cyclic=True, halo=halo)
         for _ in range(STEPS):
@@ -79,9 +87,10 @@ def _worker(rank, world, port, kind, halo, outdir):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("even", [True, False], ids=["even", "uneven"])
 @pytest.mark.parametrize("halo", ["peer", "nccl"])
 @pytest.mark.parametrize("kind", ["analytic", "random"])
-def test_two_rank_overlapped_steps_match_single_gpu_bit_for_bit(kind, halo):
+def test_two_rank_overlapped_steps_match_single_gpu_bit_for_bit(kind, halo, even):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs two CUDA devices")
     import torch.multiprocessing as mp
@@ -91,7 +100,7 @@ def test_two_rank_overlapped_steps_match_single_gpu_bit_for_bit(kind, halo):
 
     world = 2
     with tempfile.TemporaryDirectory() as outdir:
-        mp.spawn(_worker, args=(world, _free_port(), kind, halo, outdir), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), kind, halo, outdir, even), nprocs=world, join=True)
         # single-GPU reference: the global state, plain fused step + the cyclic wrap of enforce_boundaries
         st = global_state(kind)
         g = IsoState.from_numpy(st, "cuda:0")

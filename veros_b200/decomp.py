@@ -25,6 +25,32 @@ def slab_bounds(nx_global, world_size, rank):
     return rank * n, (rank + 1) * n
 
 
+def balanced_slab_bounds(costs, world_size, min_width=8):
+    """Cut points of `world_size` contiguous x-slabs of unequal width whose summed plane costs are as equal as a
+    greedy prefix partition gets them: returns [(x0, x1)] per rank.  `costs[i]` is the relative cost of interior
+    plane i (e.g. wet cells + a fraction of the dry ones: land and deep-sea planes are not equally expensive).
+    The reference insists on equal widths (veros/distributed.py:124-128); nothing in the path needs that -- a slab only
+    has to be at least `min_width` planes wide (halo reach 2, overlap strips 4)."""
+    import numpy as np
+
+    costs = np.asarray(costs, dtype=np.float64)
+    n = len(costs)
+    if world_size * min_width > n:
+        raise ValueError(f"{n} planes cannot be cut into {world_size} slabs of at least {min_width}")
+    cum = np.concatenate([[0.0], np.cumsum(costs)])
+    cuts = [0]
+    for r in range(1, world_size):
+        target = cum[-1] * r / world_size
+        x = int(np.searchsorted(cum, target))  # first prefix reaching the target
+        if x > 0 and abs(cum[x - 1] - target) <= abs(cum[x] - target):
+            x -= 1
+        x = max(x, cuts[-1] + min_width)
+        x = min(x, n - (world_size - r) * min_width)
+        cuts.append(x)
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
+
+
 def neighbours(rank, world_size, cyclic):
     west = rank - 1 if rank > 0 else (world_size - 1 if cyclic else None)
     east = rank + 1 if rank < world_size - 1 else (0 if cyclic else None)

@@ -122,6 +122,45 @@ def vertical_grid(nz, depth=5000.0, dz_top=10.0):
     return dzt, dzw, zt
 
 
+def _analytic_kbot(ig, X2, Y2, dzt, nz, nxg, M, rng):
+    """Bathymetry of the analytic ocean: ridges and basins, continents near fixed longitudes, a few random islands.
+    `ig`: global interior index of every local column; X2 / Y2: longitude / latitude (radians) broadcastable to (N, M)."""
+    depth = 5000.0 * (0.55 + 0.25 * np.cos(2 * X2) * np.cos(3 * Y2) + 0.2 * np.sin(5 * X2 + Y2))
+    land = (np.cos(X2 - 0.6) > 0.93) & (np.abs(Y2) < 1.0)
+    land |= (np.cos(X2 - 3.5) > 0.95) & (Y2 > -0.6)
+    cell_top = np.cumsum(dzt) - dzt.sum()  # zw
+    # kbot-1 = first level (from the bottom) whose top lies above the sea floor
+    kb = 1 + (cell_top[None, None, :] <= -depth[..., None]).sum(axis=-1)
+    kbot = np.clip(kb, 1, nz - 1).astype(np.int32)
+    kbot[land] = 0
+    jj, ii = rng.integers(4, max(5, M - 4), 12), rng.integers(0, nxg, 12)
+    for a, b in zip(ii, jj):
+        kbot[(ig == a), b] = 0
+    kbot[:, :2] = 0
+    kbot[:, -2:] = 0
+    return kbot
+
+
+def analytic_plane_costs(name, dry_cost=0.34, **overrides):
+    """Relative cost of every interior x-plane of a named analytic workload, for load-balanced slab cuts: wet cells
+    count 1, dry cells `dry_cost` (masked faces only store zeros and dry cells are skipped by the update, measured on
+    B200: profiles/r02_scaling.md).  Only the 2-D bathymetry is generated (milliseconds, any grid size)."""
+    cfg = dict(WORKLOADS[name])
+    cfg.update(overrides)
+    nxg, ny, nz = cfg["nx"], cfg["ny"], cfg["nz"]
+    M = ny + 4
+    lat_south, lat_north = cfg.get("lat_south", -78.0), cfg.get("lat_north", 78.0)
+    rng = np.random.default_rng(cfg.get("seed", 0))
+    ig = np.arange(nxg)
+    lon = (ig + 0.5) * (360.0 / nxg)
+    lat = lat_south + (np.arange(M) - 2 + 0.5) * ((lat_north - lat_south) / ny)
+    dzt, _, _ = vertical_grid(nz)
+    kbot = _analytic_kbot(ig, np.deg2rad(lon)[:, None], np.deg2rad(lat)[None, :], dzt, nz, nxg, M, rng)
+    wet = np.where(kbot > 0, nz - (kbot - 1), 0)[:, 2:-2].sum(axis=1).astype(np.float64)  # wet cells per plane
+    total = float(ny * nz)
+    return wet + dry_cost * (total - wet)
+
+
 def analytic_state(nx, ny, nz, eq_of_state_type=5, enable_conserve_energy=True, dt_tracer=86400.0 / 2,
                    K_iso_0=1000.0, K_iso_steep=500.0, iso_slopec=1e-3, iso_dslope=1e-3, lat_south=-78.0,
                    lat_north=78.0, seed=0, x_offset=0, nx_global=None):
@@ -164,20 +203,7 @@ def analytic_state(nx, ny, nz, eq_of_state_type=5, enable_conserve_energy=True, 
     st["int_drhodT"] = np.repeat((-rho0 * betaT * Z * (1.0 + 0.02 * temp))[..., None], 3, axis=-1)
     st["int_drhodS"] = np.repeat((rho0 * betaS * Z * (1.0 + 0.001 * (salt - 35.0)))[..., None], 3, axis=-1)
 
-    # bathymetry: ridges and basins, continents near fixed longitudes, a few random islands
-    depth = 5000.0 * (0.55 + 0.25 * np.cos(2 * X[..., 0]) * np.cos(3 * Y[..., 0]) + 0.2 * np.sin(5 * X[..., 0] + Y[..., 0]))
-    land = (np.cos(X[..., 0] - 0.6) > 0.93) & (np.abs(Y[..., 0]) < 1.0)
-    land |= (np.cos(X[..., 0] - 3.5) > 0.95) & (Y[..., 0] > -0.6)
-    cell_top = np.cumsum(dzt) - dzt.sum()  # zw
-    # kbot-1 = first level (from the bottom) whose top lies above the sea floor
-    kb = 1 + (cell_top[None, None, :] <= -depth[..., None]).sum(axis=-1)
-    kbot = np.clip(kb, 1, nz - 1).astype(np.int32)
-    kbot[land] = 0
-    jj, ii = rng.integers(4, max(5, M - 4), 12), rng.integers(0, nxg, 12)
-    for a, b in zip(ii, jj):
-        kbot[(ig == a), b] = 0
-    kbot[:, :2] = 0
-    kbot[:, -2:] = 0
+    kbot = _analytic_kbot(ig, X[..., 0], Y[..., 0], dzt, nz, nxg, M, rng)
     st["kbot"] = kbot
     st["maskT"], st["maskU"], st["maskV"], st["maskW"] = masks_from_kbot(kbot, nz, cyclic_x=False)
     st["tau"], st["taup1"] = 1, 2
