@@ -545,8 +545,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
+        import datetime
+
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # a collective that some rank never joins must fail, not hang the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
 
     def barrier():
         if world > 1:
@@ -592,8 +595,12 @@ def main():
     # state replicas: consecutive steps touch different memory, so nothing is served from L2
     probe = IsoState.from_numpy(st, dev)
     state_bytes = sum(t.numel() * t.element_size() for t in vars(probe.variables).values() if hasattr(t, 'numel'))
-    replicas = args.replicas or max(2, min(8, int(3 * L2_BYTES / state_bytes) + 1))
-    if state_bytes > 4e9 and not args.replicas:
+    # EVERY decision that changes which collectives / exchanges a rank takes part in is made on values all ranks
+    # agree on (unequal slab widths give the ranks different sizes): the largest slab decides
+    cells_max = int(max_over_ranks(float(cells)))
+    state_bytes_max = max_over_ranks(float(state_bytes))
+    replicas = args.replicas or max(2, min(8, int(3 * L2_BYTES / state_bytes_max) + 1))
+    if state_bytes_max > 4e9 and not args.replicas:
         replicas = 1  # one pass over the state already streams several L2 sizes
     states = [probe] + [IsoState.from_numpy(st, dev) for _ in range(replicas - 1)]
 
@@ -602,7 +609,7 @@ def main():
     # the step: measured on 2 GPUs, 0.25 degree strong scaling (profiles/r02_scaling.md): peer-memory exchange after
     # the step 7.23 ms/step (98 % efficient) vs overlapped 8.19 ms (the two extra strip passes cost more than the
     # ~20 us exchange they hide); with pack + NCCL + unpack on >= 3 M-cell slabs the overlap wins (round 1).
-    overlap = world > 1 and (args.overlap == "on" or (args.overlap == "auto" and args.halo == "nccl" and cells >= 3_000_000))
+    overlap = world > 1 and (args.overlap == "on" or (args.overlap == "auto" and args.halo == "nccl" and cells_max >= 3_000_000))
 
     def build_exchange(halo):
         steppers_ = [decomp.OverlappedStepper(s, cyclic=cyclic, halo=halo) for s in states] if overlap else None
@@ -825,7 +832,7 @@ def main():
 
     # ---- end to end: host buffers in, host buffers out ----------------------------------------------
     hs = None
-    if args.no_e2e or cells > 20_000_000:
+    if args.no_e2e or cells_max > 20_000_000:
         clocks = sampler.stop() if rank == 0 else None
         e2e = None  # the pinned staging buffers of this leg would be tens of GB
     else:

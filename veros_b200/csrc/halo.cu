@@ -60,6 +60,22 @@ __device__ __forceinline__ int flag_load(const int* p) {
     return v;
 }
 
+// Bounded wait: ranks that disagree about the number of exchanges (a host-side bug) must produce an error, not a GPU
+// that spins until the job is killed.
+__device__ __forceinline__ void flag_wait(const int* p, int seq) {
+    if (flag_load(p) >= seq) return;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    unsigned spins = 0;
+    while (flag_load(p) < seq) {
+        __nanosleep(100);
+        if ((++spins & 0x3ffu) == 0u) {
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            if (t - t0 > 30000000000ull) __trap();  // 30 s
+        }
+    }
+}
+
 struct PeerHalo {
     double* mine[4];
     double* west[4];  // the west neighbour's arrays (null: no neighbour on that side)
@@ -76,8 +92,8 @@ halo_put_kernel(PeerHalo h, int N, int N_west, size_t plane, int nlev, int level
             if (has_w) flag_store(west_flags + 1, seq);  // I am their east neighbour
             if (has_e) flag_store(east_flags + 0, seq);
         }
-        if (has_w) while (flag_load(my_flags + 0) < seq) {}
-        if (has_e) while (flag_load(my_flags + 1) < seq) {}
+        if (has_w) flag_wait(my_flags + 0, seq);
+        if (has_e) flag_wait(my_flags + 1, seq);
     }
     __syncthreads();
     const size_t per_field = 2 * plane;
@@ -98,8 +114,8 @@ halo_put_kernel(PeerHalo h, int N, int N_west, size_t plane, int nlev, int level
             __threadfence_system();
             if (has_w) flag_store(west_flags + 3, seq);
             if (has_e) flag_store(east_flags + 2, seq);
-            if (has_w) while (flag_load(my_flags + 2) < seq) {}
-            if (has_e) while (flag_load(my_flags + 3) < seq) {}
+            if (has_w) flag_wait(my_flags + 2, seq);
+            if (has_e) flag_wait(my_flags + 3, seq);
         }
     }
 }
