@@ -25,19 +25,25 @@ FULL_METRICS = [
 
 
 def launches(path):
+    """Per-kernel device time (+ DRAM bytes when the list was taken with dram__bytes_read/write.sum too)."""
     rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
     hdr = rows[0]
-    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-    tot = collections.OrderedDict()
+    ki, vi, mi, ii = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name"), hdr.index("ID")
+    per_launch = collections.OrderedDict()
     for r in rows[1:]:
         name = r[ki].split("(")[0].replace("void ", "")
-        t = tot.setdefault(name, [0, 0.0])
+        per_launch.setdefault((r[ii], name), {})[r[mi]] = float(r[vi].replace(",", ""))
+    tot = collections.OrderedDict()
+    for (_, name), m in per_launch.items():
+        t = tot.setdefault(name, [0, 0.0, 0.0, 0.0])
         t[0] += 1
-        t[1] += float(r[vi].replace(",", ""))
+        t[1] += m.get("gpu__time_duration.sum", 0.0)
+        t[2] += m.get("dram__bytes_read.sum", 0.0)
+        t[3] += m.get("dram__bytes_write.sum", 0.0)
     total = sum(v[1] for v in tot.values())
-    print(f"{'kernel':60s} {'launches':>8s} {'avg us':>10s} {'share':>7s}")
-    for name, (n, ns) in tot.items():
-        print(f"{name[:60]:60s} {n:8d} {ns / n / 1e3:10.2f} {100 * ns / total:6.1f}%")
+    print(f"{'kernel':60s} {'launches':>8s} {'avg us':>10s} {'share':>7s} {'DRAM rd MB':>11s} {'DRAM wr MB':>11s}")
+    for name, (n, ns, rd, wr) in tot.items():
+        print(f"{name[:60]:60s} {n:8d} {ns / n / 1e3:10.2f} {100 * ns / total:6.1f}% {rd / n / 1e6:11.1f} {wr / n / 1e6:11.1f}")
 
 
 def full(rep):
