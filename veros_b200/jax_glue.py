@@ -27,6 +27,11 @@ TARGETS = {
     "veros_b200_iso_diffusion_f64": "veros_b200_iso_diffusion_f64",
     "veros_b200_iso_step_f64": "veros_b200_iso_step_f64",
     "veros_b200_vertmix_tempsalt_f64": "veros_b200_vertmix_tempsalt_f64",
+    # neighbours of the path
+    "veros_b200_implicit_vert_friction_f64": "veros_b200_implicit_vert_friction_f64",
+    "veros_b200_advect_tempsalt_f64": "veros_b200_advect_tempsalt_f64",
+    "veros_b200_set_eke_diffusivities_f64": "veros_b200_set_eke_diffusivities_f64",
+    "veros_b200_iso_diag_streamfunction_f64": "veros_b200_iso_diag_streamfunction_f64",
     # the reference's own target names, served by the z-major compatible kernels (shim below)
     "tdma_cuda_double": "veros_b200_tdma_zmajor_f64",
     "tdma_cuda_float": "veros_b200_tdma_zmajor_f32",
@@ -148,6 +153,13 @@ def _primitives():
     _prims["solve"] = _make_primitive("veros_b200_solve_implicit_f64", 0, True, False, None, fresh_like=(0,))
     # temp, salt updated in place; dtemp_vmix, dsalt_vmix fresh, shaped like kappaH (operand 3)
     _prims["vertmix"] = _make_primitive("veros_b200_vertmix_tempsalt_f64", 2, True, False, None, fresh_like=(3, 3))
+    # u, v, du_mix, dv_mix, K_diss_v in place + scratch of 2 N M nz doubles
+    _prims["friction"] = _make_primitive("veros_b200_implicit_vert_friction_f64", 5, True, True,
+                                         lambda d: 16 * _lib.ColumnDescriptor.from_buffer_copy(bytes(d)).nx_tot *
+                                         _lib.ColumnDescriptor.from_buffer_copy(bytes(d)).ny_tot *
+                                         _lib.ColumnDescriptor.from_buffer_copy(bytes(d)).nz)
+    _prims["advect"] = _make_primitive("veros_b200_advect_tempsalt_f64", 4, True, False, None)  # temp, salt, dtemp, dsalt
+    _prims["streamfunction"] = _make_primitive("veros_b200_iso_diag_streamfunction_f64", 2, False, False, None)  # B1_gm, B2_gm
     return _prims
 
 
@@ -271,7 +283,28 @@ def make_replacements():
             res.pop("P_diss_iso")
         return KernelOutput(**res)
 
-    return dict(isoneutral_fused_step=isoneutral_fused_step,
+    @veros_kernel
+    def implicit_vert_friction(state):
+        """veros/core/friction.py:92-205 as one custom call (coefficient assembly fused into the column solves)."""
+        vs, st = state.variables, state.settings
+        N, M, nz = vs.kappaM.shape
+        desc = _lib.ColumnDescriptor(nx_tot=N, ny_tot=M, nz=nz, flags=0, dt=st.dt_mom)
+        ops = [vs.u, vs.v, vs.du_mix, vs.dv_mix, vs.K_diss_v, _i32(vs.tau), _i32(vs.taup1), vs.kappaM, _u8(vs.maskU),
+               _u8(vs.maskV), vs.kbot.astype(jnp.int32), vs.dzt, vs.dzw, vs.dxt, vs.dxu, vs.area_v, vs.area_t]
+        u, v, du_mix, dv_mix, K_diss_v, _ = P["friction"].bind(*ops, descriptor=bytes(desc))
+        return KernelOutput(u=u, v=v, du_mix=du_mix, dv_mix=dv_mix, K_diss_v=K_diss_v)
+
+    @veros_kernel
+    def isoneutral_diag_streamfunction_kernel(state):
+        """veros/core/isoneutral/isoneutral.py:232-258."""
+        vs = state.variables
+        N, M, nz = vs.K_gm.shape
+        desc = _lib.ColumnDescriptor(nx_tot=N, ny_tot=M, nz=nz, flags=0, dt=0.0)
+        B1, B2 = P["streamfunction"].bind(vs.K_gm, vs.Ai_ez, vs.Ai_nz, vs.B1_gm, vs.B2_gm, descriptor=bytes(desc))
+        return KernelOutput(B1_gm=B1, B2_gm=B2)
+
+    return dict(isoneutral_fused_step=isoneutral_fused_step, implicit_vert_friction=implicit_vert_friction,
+                isoneutral_diag_streamfunction_kernel=isoneutral_diag_streamfunction_kernel,
                 vertmix_tempsalt=vertmix_tempsalt, isoneutral_diffusion_pre=isoneutral_diffusion_pre, isoneutral_diffusion=isoneutral_diffusion,
                 isoneutral_skew_diffusion=isoneutral_skew_diffusion, solve_implicit=solve_implicit,
                 solve_tridiagonal=solve_tridiagonal)
@@ -307,6 +340,11 @@ def install(fused=True):
     import veros.core.thermodynamics as thermodynamics
 
     thermodynamics.vertmix_tempsalt = r["vertmix_tempsalt"]  # looked up as a module global at :440
+    import veros.core.friction as friction_mod
+    import veros.core.isoneutral.isoneutral as iso_mod
+
+    friction_mod.implicit_vert_friction = r["implicit_vert_friction"]  # called at friction.py:986-987
+    iso_mod.isoneutral_diag_streamfunction_kernel = r["isoneutral_diag_streamfunction_kernel"]  # isoneutral.py:269
     from . import facade
 
     if fused:
