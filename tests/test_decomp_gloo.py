@@ -20,7 +20,16 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, cyclic, out):
+def _bounds(nxg, world, even):
+    """Equal-width slabs (the reference's decomposition) or the unequal widths a cost-balanced cut produces."""
+    from veros_b200 import decomp
+
+    if even:
+        return [decomp.slab_bounds(nxg, world, r) for r in range(world)]
+    return decomp.balanced_slab_bounds(np.r_[np.ones(nxg // 2) * 3.0, np.ones(nxg - nxg // 2)], world, min_width=4)
+
+
+def _worker(rank, world, port, cyclic, out, even=True):
     import sys
 
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -33,7 +42,7 @@ def _worker(rank, world, port, cyclic, out):
     try:
         nxg, ny = 16, 12
         oracle.set_num_threads(1)
-        x0, x1 = decomp.slab_bounds(nxg, world, rank)
+        x0, x1 = _bounds(nxg, world, even)[rank]
         st = synthetic.make_workload("global_4deg", nx=x1 - x0, ny=ny, x_offset=x0, nx_global=nxg)
         taup1 = int(st["taup1"])
         oracle.isoneutral_step(st)
@@ -46,15 +55,17 @@ def _worker(rank, world, port, cyclic, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("even", [True, False], ids=["even", "uneven"])
 @pytest.mark.parametrize("cyclic", [True, False])
-def test_two_slabs_with_halo_exchange_match_single_process(cyclic):
+def test_two_slabs_with_halo_exchange_match_single_process(cyclic, even):
     from oracle import oracle
     from veros_b200 import synthetic
 
     world, nxg, ny = 2, 16, 12
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), cyclic, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), cyclic, out, even), nprocs=world, join=True)
+    assert even or out[0]["x1"] - out[0]["x0"] != out[1]["x1"] - out[1]["x0"]  # the uneven case really is uneven
 
     full = synthetic.make_workload("global_4deg", nx=nxg, ny=ny)
     before = {k: full[k].copy() for k in ("temp", "salt", "K_33")}

@@ -163,3 +163,36 @@ def test_balanced_slab_bounds_equalise_cost_and_respect_min_width():
     st = synthetic.make_workload("global_4deg")
     wet = st["maskT"][2:-2, 2:-2].reshape(90, -1).sum(axis=1)
     assert np.allclose(synthetic.analytic_plane_costs("global_4deg"), wet + 0.34 * (40 * 15 - wet))
+
+
+def test_advance_time_rotates_device_scalars_host_copies_and_views():
+    """the time-level indices the kernels read (device scalars) and the ones the plumbing uses (host copies,
+    also in sub-slab views) must change together.  Runs on CPU tensors: IsoState only needs them as buffers."""
+    from veros_b200 import synthetic
+    from veros_b200.state import IsoState
+
+    st = synthetic.make_workload("global_4deg", nx=12, ny=6)
+    gs = IsoState.from_numpy(st, "cpu")
+    sub = gs.subslab(0, 8)
+    seen = []
+    for _ in range(4):
+        vs = gs.variables
+        assert int(vs.tau.item()) == vs.tau_host and int(vs.taup1.item()) == vs.taup1_host
+        assert sub.variables.taup1_host == vs.taup1_host and sub.variables.tau is vs.tau  # views share the scalars
+        assert len({vs.tau_host, vs.taup1_host, 3 - vs.tau_host - vs.taup1_host}) == 3
+        seen.append((vs.tau_host, vs.taup1_host))
+        gs.advance_time()
+    assert seen[0] == (1, 2) and seen[1] == (2, 0) and seen[2] == (0, 1) and seen[3] == seen[0]  # veros.py: taum1, tau, taup1 = tau, taup1, taum1
+
+
+def test_jax_glue_module_imports_without_jax_and_targets_are_exported():
+    """jax_glue.py imports jax lazily (there is none in this image): the module itself must load, every XLA target
+    name must map to a symbol the library exports, and install() must refuse to run without the JAX backend."""
+    from veros_b200 import _lib, build, jax_glue
+
+    build.build()
+    L = _lib.lib()
+    for target, symbol in jax_glue.TARGETS.items():
+        assert hasattr(L, symbol), (target, symbol)
+    assert set(jax_glue.TARGETS.values()) >= set(_lib.OPS)
+    assert jax_glue.build_tridiag_descriptor(3, 5) == bytes(_lib.TridiagDescriptor(num_systems=3, system_depth=5))
