@@ -10,6 +10,7 @@ veros/settings.py that the hot path touches, so host code reads like the referen
 Arrays are torch CUDA tensors used purely as device buffers (dtype / shape / data_ptr); no torch
 arithmetic is ever applied to them.
 """
+import weakref
 from collections import namedtuple
 from types import SimpleNamespace
 
@@ -62,6 +63,7 @@ class IsoState:
         self._dummy = torch.zeros(8, dtype=torch.float64, device=device)
         self.ring_flags = 0  # VEROS_B200_FLAG_NO_WEST_RING / _NO_EAST_RING for x-sub-slab views
         self.tuning_flags = 0  # VEROS_B200_FLAG_PRE_SINGLE / _PRE_SPLIT ...: kernel-variant knobs (tests, tuning)
+        self._views = weakref.WeakSet()  # sub-slab views: advance_time() keeps their host-side time levels in step
 
     # ---- construction --------------------------------------------------------------------------
     @classmethod
@@ -150,7 +152,7 @@ class IsoState:
         vs.tau_host, vs.taup1_host = taup1, taum1
         vs.tau.fill_(taup1)
         vs.taup1.fill_(taum1)
-        for sub in getattr(self, "_views", ()):
+        for sub in list(self._views):
             sub.variables.tau_host, sub.variables.taup1_host = taup1, taum1
 
     # ---- helpers --------------------------------------------------------------------------------
@@ -186,9 +188,7 @@ class IsoState:
         sub.tuning_flags = self.tuning_flags
         sub.ring_flags = (0 if i0 == 0 else _lib.FLAG_NO_WEST_RING) | (0 if i1 == N else _lib.FLAG_NO_EAST_RING)
         sub._parent = self
-        if not hasattr(self, "_views"):
-            self._views = []
-        self._views.append(sub)  # advance_time() keeps the views' host-side time levels in step
+        self._views.add(sub)
         return sub
 
     def workspace(self, nbytes):
